@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py — headline measurement of the per-ray geodesic hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3], the configuration its metric is quoted on): one 3840x2160 frame of the
+default config.py scene (observer (30,0,0), fov 80 deg, r_s = 2, r_max = 31, delta = 0.01, step cap 200 000,
+omega_eff = 1.0, full-sky patch) over a synthetic sky texture.  A "step" is one frame.  With N ranks the
+pixel rows are sharded row-cyclically (fixed total work => "strong" scaling) and each step ends with ONE
+all_gather of rgb+class over NCCL.
+
+One JSON line on rank 0.  `value` = geodesic steps/s with inputs resident in HBM (CUDA events on the launch
+stream, max over ranks); `e2e` = the same metric through the host-buffer C-ABI call (pinned host texture in,
+rgb/class out, copies inside the timed region); `roofline` against the FP64 FMA peak measured in this run;
+`cpu_baseline` = the CPU oracle (oracle/, a port of the reference's arithmetic) on a bounded row sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "schwarzchild-einsteinpy-raytracing_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+ALGO_FLOP_PER_STEP = 312        # 268 add/mul (FMA = 2) + 36 div + 8 sin/cos
+NOMINAL_FP64_TFLOPS = 37.2      # 148 SM x 64 lanes x 2 x 1.965 GHz
+
+
+def synthetic_sky(h, w, seed=0):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    t = np.empty((h, w, 3), np.uint8)
+    t[..., 0] = (xx * 255 // max(w - 1, 1)).astype(np.uint8)
+    t[..., 1] = (yy * 255 // max(h - 1, 1)).astype(np.uint8)
+    t[..., 2] = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    return t
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def sample_rows(h, nrows):
+    """Evenly spaced rows of the frame (a representative mix of captured / near-critical / corner rays)."""
+    nrows = max(1, min(h, nrows))
+    return np.unique(np.floor((np.arange(nrows) + 0.5) * h / nrows).astype(int))
+
+
+def cpu_reference_leg(args, nthreads, target_seconds):
+    """The reference's CPU arithmetic (oracle port, OpenMP over all host cores) on a bounded row sample."""
+    from oracle import oracle as O
+    O.build()
+    nthreads = nthreads or (os.cpu_count() or 1)
+    sc = O.make_scene(height=args.height, width=args.width)
+    tex = synthetic_sky(args.height, args.width)
+    # ~1.3 us per step per core for the literal port, ~5.9 k steps per ray
+    rays = target_seconds * nthreads / (1.3e-6 * 5900)
+    rows = sample_rows(args.height, int(round(rays / args.width)))
+    def one():
+        t0 = time.perf_counter()
+        steps = 0
+        for r in rows:
+            out = O.render(sc, tex, int(r), int(r) + 1, 1, nthreads=nthreads, extras=False)
+            steps += int(out["nsteps"].sum())
+        return steps, time.perf_counter() - t0
+    return one, rows, nthreads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    one, rows, nthreads = cpu_reference_leg(args, 0, target_seconds=8.0)
+    for _ in range(args.warmup):
+        one()
+    tot_steps, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        s, t = one()
+        tot_steps += s; tot_t += t
+    value = tot_steps / tot_t
+    sample = f"{len(rows)} evenly spaced rows of the {args.width}x{args.height} frame per step ({len(rows) * args.width} rays)"
+    line = {
+        "impl": "reference", "metric": "geodesic_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "mrays_per_s": 1e-6 * len(rows) * args.width * args.steps / tot_t,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n):
+    return {"workload": f"{args.width}x{args.height} Schwarzschild lensing frame, default config.py scene "
+                        f"(obs (30,0,0), fov 80deg, r_max 31, delta 0.01, steps cap 200000, omega_eff 1.0, full-sky patch), "
+                        f"synthetic sky texture", "height": args.height, "width": args.width,
+            "sharding": f"row-cyclic over {n} rank(s), one all_gather of rgb+class per frame" if n > 1 else "single GPU",
+            "l2": "L2 flushed (256 MiB memset) between timed frames"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import schw_b200
+    from schw_b200.multigpu import gather_row_blocks, shard_rows, rows_of
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    h, w = args.height, args.width
+    hd = schw_b200.Handle(local_rank)
+    scene = schw_b200.make_scene(height=h, width=w)
+    tex_host = torch.from_numpy(synthetic_sky(h, w)).pin_memory()
+    rb, re, rs = shard_rows(h, rank, world)
+    nloc = rows_of(h, rank, world)
+    max_rows = (h + world - 1) // world
+    d_tex = tex_host.to(dev, non_blocking=False)
+    # packed output block (rows, 4w): rgb then class, the message of the single all_gather
+    d_out = torch.zeros((max_rows, 4 * w), dtype=torch.uint8, device=dev)
+    d_rgb = torch.empty((max_rows, w, 3), dtype=torch.uint8, device=dev)
+    d_cls = torch.empty((max_rows, w), dtype=torch.uint8, device=dev)
+    d_all = torch.empty((world, max_rows, 4 * w), dtype=torch.uint8, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        hd.render_dev(scene, d_tex.data_ptr(), rb, re, rs, d_rgb.data_ptr(), d_cls.data_ptr(), stream=stream)
+        if world > 1:
+            d_out[:, :3 * w] = d_rgb.view(max_rows, 3 * w)
+            d_out[:, 3 * w:] = d_cls
+            dist.all_gather_into_tensor(d_all, d_out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # FP64 FMA peak of this device, measured before the run (roofline denominator)
+    peak_tflops, _ = hd.fp64_peak_probe()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    steps_per_frame_local = hd.last_total_steps()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                                   # L2 flush, outside the per-step events
+        ev[k][0].record()
+        step_device()
+        ev[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    km, _ = hd.last_kernel_ms()
+    kern_ms.append(km)
+
+    # ---- e2e: the host-buffer C-ABI call a user makes (texture H2D + outputs D2H inside the timed region) ----
+    def step_e2e():
+        out = hd.render(scene, tex_host.numpy(), rb, re, rs)
+        if world > 1:
+            packed = np.concatenate([out["rgb"].reshape(nloc, 3 * w), out["cls"]], axis=1)
+            return gather_row_blocks(packed, h, world, rank, dev)
+        return out["rgb"]
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+
+    stats = torch.tensor([dev_ms, e2e_s, float(steps_per_frame_local), kern_ms[-1]], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s, kernel_ms = mx[0].item(), mx[1].item(), mx[3].item()
+        steps_per_frame = sm[2].item()
+    else:
+        kernel_ms = kern_ms[-1]
+        steps_per_frame = float(steps_per_frame_local)
+
+    if rank == 0:
+        value = steps_per_frame * args.steps / (dev_ms * 1e-3)
+        e2e_value = steps_per_frame * args.steps / e2e_s
+        # roofline of the dominant kernel (persistent_rays<RenderJob>), per launch, this rank's shard
+        achieved = ALGO_FLOP_PER_STEP * steps_per_frame_local / (kern_ms[-1] * 1e-3) / 1e12
+        line = {
+            "metric": "geodesic_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "frame_ms": dev_ms / args.steps, "mrays_per_s": 1e-6 * h * w * args.steps / (dev_ms * 1e-3),
+            "steps_per_frame": steps_per_frame, "wall_s_timed_region": t_wall,
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": int(h * w * 3) * world,
+                    "d2h_bytes_per_step": int(4 * w * h), "frame_ms": 1e3 * e2e_s / args.steps},
+            "gpu_launches": args.steps * world,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tflops, "traffic": None,
+                         "peak_source": "measured in this run (schw_fp64_peak_probe: register-resident DFMA chains); "
+                                        f"nominal {NOMINAL_FP64_TFLOPS} TFLOP/s",
+                         "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
+                         "algorithmic_flop_per_step": ALGO_FLOP_PER_STEP, "kernel": "persistent_rays<RenderJob>",
+                         "kernel_ms": kern_ms[-1]},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            one, rows, nthreads = cpu_reference_leg(args, 0, target_seconds=15.0)
+            s, t = one()
+            line["cpu_baseline"] = {"value": s / t, "unit": "steps/s", "cores": nthreads, "kind": "port",
+                                    "sample": f"{len(rows)} evenly spaced rows of the same frame ({len(rows) * w} rays, {s} steps, {t:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+/*
+ * schw_b200.h — C ABI of libschw_b200.so, the B200 (sm_100a) replacement for the per-ray
+ * geodesic hot path of ryanchen2134/schwarzchild-einsteinpy-raytracing.
+ *
+ * Plain C: opaque handle, pointers and sizes only; no torch / numpy / C++ types.
+ * Every entry point names the reference interface it replaces (file:line relative to the
+ * reference checkout).  All functions return 0 on success or a negative SCHW_E_* code;
+ * schw_last_error() returns a thread-local human-readable message for the last failure.
+ *
+ * Threading: a handle owns one CUDA stream and its scratch buffers; calls on one handle must
+ * not overlap (thread-compatible, not thread-safe).  Different handles are independent.
+ * There is no CPU fallback: every compute entry point fails with SCHW_E_CUDA when no
+ * sm_100-class device is usable.
+ *
+ * Pointer residency: entry points without a suffix take HOST pointers and do the H2D/D2H
+ * copies themselves on the handle's stream (synchronous on return, like the reference's
+ * implicit Numba transfers at cuda_geodesic.py:644,652).  `_dev` entry points take DEVICE
+ * pointers (e.g. torch tensors' data_ptr()) and only enqueue work on the given stream.
+ */
+#ifndef SCHW_B200_H
+#define SCHW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCHW_ABI_VERSION 1
+
+/* error codes */
+#define SCHW_OK            0
+#define SCHW_E_INVALID    -1   /* bad argument (null pointer, negative size, ...)                      */
+#define SCHW_E_CUDA       -2   /* CUDA runtime error or no usable device                               */
+#define SCHW_E_HORIZON    -3   /* observer inside the horizon: reference raises ValueError   (simulation/utils.py:67-68)  */
+#define SCHW_E_NULLCOND   -4   /* negative discriminant:        reference raises RuntimeError (simulation/utils.py:80-81)  */
+#define SCHW_E_RAYPLANE   -5   /* ray not in the equatorial plane after rotation: AssertionError (simulation/utils.py:113,126) */
+#define SCHW_E_NOMEM      -6
+
+/* ray classes, in the order of the reference's `collision` strings (simulation/raytracing.py:210-272) */
+#define SCHW_CLS_BH               0   /* 'bh'               */
+#define SCHW_CLS_NUMERICAL_ERROR  1   /* 'numerical error'  */
+#define SCHW_CLS_ESCAPE_BG        2   /* 'escape_bg'        */
+#define SCHW_CLS_ESCAPE_NO_PATCH  3   /* 'escape_no_patch'  */
+#define SCHW_CLS_IN_DOMAIN        4   /* 'in_domain'        */
+
+typedef struct schw_handle schw_handle;
+
+/* Scene = the arguments of run_manual_simulation (simulation/raytracing.py:16-24) plus the
+ * Observer / BlackHole fields it reads (simulation/blackhole.py:4-25). */
+typedef struct schw_scene {
+    double  obs[3];              /* observer.position; the reference's camera axes are hard-wired to an
+                                    observer on the +x axis (raytracing.py:60-72)                          */
+    double  fov;                 /* observer.fov, radians                                                  */
+    int32_t height, width;       /* observer.image_size = (h, w)                                           */
+    double  mass;                /* bh.mass (rs = 2*mass, blackhole.py:13)                                 */
+    double  r_max;               /* boundary_radius: integrator r_max (raytracing.py:118) and escape test (:216) */
+    int64_t steps;               /* step cap (cuda_geodesic.py:596)                                        */
+    double  delta;               /* affine step                                                            */
+    double  omega;               /* FANTASY coupling actually used; run_manual_simulation always uses 1.0
+                                    (raytracing.py:118 drops its omega argument, cuda_geodesic.py:632)     */
+    double  patch_center_theta, patch_center_phi, patch_size_theta, patch_size_phi;   /* radians          */
+    int32_t flip_theta, flip_phi;
+    int32_t has_texture;         /* 0 <=> background_path is None (raytracing.py:217,265-268)              */
+    int32_t _pad;
+} schw_scene;
+
+/* Optional per-ray outputs of schw_render*; any member may be NULL.  All arrays are indexed by the
+ * packed ray number k = (visited_row_index * width + j).  */
+typedef struct schw_ray_outputs {
+    double  *final_q;     /* (n,4)  q1 = (t,r,theta,phi) at termination            (raytracing.py:181-183)   */
+    double  *ic;          /* (n,9)  p0_t,p0_r,p0_th,p0_ph, alpha0, beta, h_r,h_theta,h_phi (utils.py:141)     */
+    double  *hit;         /* (n,2)  th_hit, ph_hit as written to photon_data.csv    (raytracing.py:276)       */
+    int32_t *texel;       /* (n,2)  (u,v) texture indices, (-1,-1) when no lookup   (raytracing.py:241-245)   */
+    int32_t *nsteps;      /* (n,)   integrator steps taken                                                     */
+} schw_ray_outputs;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int  schw_abi_version(void);
+const char *schw_last_error(void);
+/* device < 0 selects the current device.  Replaces the implicit Numba context creation. */
+int  schw_create(int device, schw_handle **out);
+int  schw_destroy(schw_handle *h);
+/* name (<=255 chars), SM count, SM clock in kHz of the handle's device */
+int  schw_device_info(schw_handle *h, char *name, int name_cap, int *sm_count, int *clock_khz);
+/* CUDA-event duration (ms) of the kernels enqueued by the last compute call on this handle,
+ * measured on the stream they were launched on; and how many kernels that call launched. */
+int  schw_last_kernel_ms(schw_handle *h, float *ms, int *launches);
+
+/* ---- stage 3+4: the integrator --------------------------------------------------------------
+ * Replaces CUDASchwarzschildIntegrator.integrate_batch (simulation/cuda_geodesic.py:639-645,
+ * kernel :579-602).  q0s,p0s: (n,4) f64 C-contiguous.  out_qs: (n,4).  out_steps: (n,) or NULL.
+ * rs = 2*mass as the class computes it (:635). */
+int  schw_integrate_batch(schw_handle *h, const double *q0s, const double *p0s, int64_t n,
+                          int64_t steps, double delta, double rs, double r_max, double omega,
+                          double *out_qs, int32_t *out_steps);
+int  schw_integrate_batch_dev(schw_handle *h, const double *d_q0s, const double *d_p0s, int64_t n,
+                              int64_t steps, double delta, double rs, double r_max, double omega,
+                              double *d_out_qs, int32_t *d_out_steps, void *cuda_stream);
+
+/* Replaces CUDASchwarzschildIntegrator.integrate_batch_full (cuda_geodesic.py:647-653, kernel
+ * :604-625).  out_traj: (n,steps,4) f64; rows after a ray's termination are zero (np.zeros, :649).
+ * out_rows: (n,) number of stored rows per ray, or NULL.  The host variant requires out_traj to be
+ * ZERO-FILLED by the caller (np.zeros) and only copies the stored rows back. */
+int  schw_integrate_batch_full(schw_handle *h, const double *q0s, const double *p0s, int64_t n,
+                               int64_t steps, double delta, double rs, double r_max, double omega,
+                               double *out_traj, int64_t *out_rows);
+
+/* ---- stages 1+2: camera rays -> initial conditions -------------------------------------------
+ * Replaces the pixel loop of run_manual_simulation (simulation/raytracing.py:60-88,98-116) and
+ * get_initial_conditions / angles_to_p_sph / build_null_4momentum_ep_sph (simulation/utils.py:
+ * 91-141,148-194,39-88) for rows row_begin, row_begin+row_stride, ... < row_end.
+ * q0s,(n,4); ic (n,9) as in schw_ray_outputs.  */
+int  schw_initial_conditions(schw_handle *h, const schw_scene *scene, int row_begin, int row_end,
+                             int row_stride, double *q0s, double *ic);
+
+/* Same for caller-supplied pixel positions: get_initial_conditions(observer_pos, pixel_pos, mass_bh=)
+ * (simulation/utils.py:91-141) as called per ray by the reference's scripts.  obs: (3,), pixels: (n,3). */
+int  schw_initial_conditions_px(schw_handle *h, const double *obs, const double *pixels, int64_t n,
+                                double mass, double *q0s, double *ic);
+
+/* ---- stage 5: rotate back, classify, texel lookup --------------------------------------------
+ * Replaces simulation/raytracing.py:166-174,181-273 on caller-supplied final states.
+ * tex: (height,width,3) u8 (the sky already resized to the frame, raytracing.py:36-37) or NULL. */
+int  schw_classify(schw_handle *h, const schw_scene *scene, const double *final_q,
+                   const double *alpha0, const double *beta, int64_t n, const uint8_t *tex,
+                   uint8_t *rgb, uint8_t *cls, double *hit, int32_t *texel);
+
+/* ---- the fused path ---------------------------------------------------------------------------
+ * Replaces run_manual_simulation's image production (simulation/raytracing.py:50-120,162-273):
+ * camera rays -> initial conditions -> FANTASY stepper with capture/escape/max-step termination
+ * -> rotate back -> classify -> equirectangular texel lookup, one launch, for rows
+ * row_begin, row_begin+row_stride, ... < row_end.  rgb: (nrows,width,3) u8; cls: (nrows,width) u8. */
+int  schw_render(schw_handle *h, const schw_scene *scene, const uint8_t *tex,
+                 int row_begin, int row_end, int row_stride,
+                 uint8_t *rgb, uint8_t *cls, const schw_ray_outputs *extra);
+/* Device-resident variant: d_tex is the (height,width,3) u8 texture already in HBM; outputs are
+ * device pointers; work is enqueued on cuda_stream (a cudaStream_t; NULL = the handle's stream). */
+int  schw_render_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex,
+                     int row_begin, int row_end, int row_stride,
+                     uint8_t *d_rgb, uint8_t *d_cls, const schw_ray_outputs *d_extra,
+                     void *cuda_stream);
+/* Sum of integrator steps over the rays of the last schw_render* / schw_integrate_batch* call on
+ * this handle (device-side counter; used for the steps/s metric). */
+int  schw_last_total_steps(schw_handle *h, uint64_t *total_steps);
+
+/* ---- next rows: flat-space comparison render ----------------------------------
+ * Replaces the pixel loop of save_no_gravity_image_with_background (simulation/background.py:
+ * 99-132): ray-sphere intersection at boundary radius r_max, truncating texel map.
+ * Uses scene->obs, fov, height, width, r_max, patch_*, flip_*.  rgb: (height,width,3) u8. */
+int  schw_flat_render(schw_handle *h, const schw_scene *scene, const uint8_t *tex, uint8_t *rgb);
+
+/* ---- measurement helper ------------------------------------------------------------------------
+ * Register-resident DFMA chains on every SM: measured FP64 FMA peak of the device in TFLOP/s
+ * (FMA = 2 flops), the denominator of the FP64 roofline (not in MEASURED_PEAKS.json). */
+int  schw_fp64_peak_probe(schw_handle *h, double *tflops, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCHW_B200_H */

@@ -47,7 +47,7 @@ def lib():
         dp, ip, bp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint8)
         i32p = C.POINTER(C.c_int32)
         L.orc_integrate_batch.argtypes = [dp, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
-                                          C.c_double, dp, ip, C.c_int]
+                                          C.c_double, dp, ip, dp, C.c_int]
         L.orc_integrate_batch_full.argtypes = [dp, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double,
                                                C.c_double, dp, dp, ip]
         L.orc_initial_conditions.argtypes = [dp, dp, C.c_int64, C.c_double, dp, dp]
@@ -86,14 +86,32 @@ def make_scene(obs=(30.0, 0.0, 0.0), fov=np.radians(80.0), height=400, width=400
     return s
 
 
-def integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega, nthreads=0):
-    """cuda_geodesic.py:639-645.  Returns (out_qs (n,4), nsteps (n,))."""
+def integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega, nthreads=0, want_rmin=False):
+    """cuda_geodesic.py:639-645.  Returns (out_qs (n,4), nsteps (n,)) [+ rmin (n,) closest approach]."""
     q0s = np.ascontiguousarray(q0s, np.float64); p0s = np.ascontiguousarray(p0s, np.float64)
     n = q0s.shape[0]
     out = np.zeros((n, 4)); ns = np.zeros(n, np.int64)
+    rmin = np.zeros(n) if want_rmin else None
     lib().orc_integrate_batch(_dp(q0s), _dp(p0s), n, int(steps), float(delta), float(rs), float(r_max),
-                              float(omega), _dp(out), _ptr(ns, C.c_int64), int(nthreads))
-    return out, ns
+                              float(omega), _dp(out), _ptr(ns, C.c_int64), _dp(rmin), int(nthreads))
+    return (out, ns, rmin) if want_rmin else (out, ns)
+
+
+def conditioning(q0s, p0s, steps, delta, rs, r_max, omega, eps=2.2e-16):
+    """Conditioning probe of the REFERENCE arithmetic: largest relative change of the final state when one
+    component of p0 is perturbed by +-eps relative (about 1 ulp).  inf where the step count changes."""
+    p0s = np.ascontiguousarray(p0s, np.float64)
+    a, na = integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega)
+    worst = np.zeros(len(a))
+    for sgn in (1.0, -1.0):
+        for comp in range(4):
+            p = p0s.copy(); p[:, comp] *= (1.0 + sgn * eps)
+            b, nb = integrate_batch(q0s, p, steps, delta, rs, r_max, omega)
+            with np.errstate(invalid="ignore"):
+                d = np.abs(a - b) / np.maximum(np.abs(a), 1.0)
+            worst = np.maximum(worst, np.nan_to_num(d.max(1), nan=np.inf))
+            worst[na != nb] = np.inf
+    return worst
 
 
 def integrate_batch_full(q0s, p0s, steps, delta, rs, r_max, omega, with_momenta=False):

@@ -151,37 +151,38 @@ static void fantasy_step_ord2(double q1[4], double p1[4], double q2[4], double p
 }
 
 /* One ray of fantasy_integrate_batch_ord2, cuda_geodesic.py:580-602.
- * Returns the number of steps taken.  state16 (nullable) receives q1,p1,q2,p2. */
+ * Returns the number of steps taken.  rmin_out (nullable) receives the smallest r either copy visited. */
 static int64_t integrate_one(const double q0[4], const double p0[4], int64_t steps, double delta,
-                             double rs, double r_max, double omega, double out_q[4], double *state16)
+                             double rs, double r_max, double omega, double out_q[4], double *rmin_out)
 {
     double q1[4], p1[4], q2[4], p2[4];
     for (int a = 0; a < 4; ++a) { q1[a] = q0[a]; p1[a] = p0[a]; q2[a] = q0[a]; p2[a] = p0[a]; }
     int64_t n = 0;
+    double rmin = q1[1];                 /* closest approach of either copy (test bookkeeping for band H) */
     for (int64_t it = 0; it < steps; ++it) {
         if (q1[1] <= 1.1 * rs || q1[1] >= r_max) break;
         fantasy_step_ord2(q1, p1, q2, p2, delta, rs, omega);
         ++n;
+        if (q1[1] < rmin) rmin = q1[1];
+        if (q2[1] < rmin) rmin = q2[1];
     }
     for (int a = 0; a < 4; ++a) out_q[a] = q1[a];
-    if (state16) {
-        memcpy(state16, q1, 32); memcpy(state16 + 4, p1, 32);
-        memcpy(state16 + 8, q2, 32); memcpy(state16 + 12, p2, 32);
-    }
+    if (rmin_out) *rmin_out = rmin;
     return n;
 }
 
 /* CUDASchwarzschildIntegrator.integrate_batch, cuda_geodesic.py:639-645 */
 int orc_integrate_batch(const double *q0s, const double *p0s, int64_t n, int64_t steps, double delta,
                         double rs, double r_max, double omega, double *out_qs, int64_t *out_steps,
-                        int nthreads)
+                        double *out_rmin, int nthreads)
 {
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
 #pragma omp parallel for schedule(dynamic, 8)
     for (int64_t i = 0; i < n; ++i) {
-        int64_t k = integrate_one(q0s + 4 * i, p0s + 4 * i, steps, delta, rs, r_max, omega, out_qs + 4 * i, 0);
+        int64_t k = integrate_one(q0s + 4 * i, p0s + 4 * i, steps, delta, rs, r_max, omega, out_qs + 4 * i,
+                                  out_rmin ? out_rmin + i : 0);
         if (out_steps) out_steps[i] = k;
     }
     return 0;

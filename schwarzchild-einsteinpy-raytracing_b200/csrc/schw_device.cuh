@@ -1,0 +1,305 @@
+// schw_device.cuh — device-side arithmetic of the Schwarzschild hot path for sm_100a.
+//
+// Everything here is FP64, one ray per thread, state in registers.  The formulas are the
+// reference's (file:line cited per function, relative to the reference checkout) but the
+// evaluation is re-derived for the B200 FP64 pipe (64 DFMA lanes / SM):
+//   * one reciprocal per Hamiltonian flow instead of nine divisions: with D = r (r-rs) sin(th),
+//     1/r, 1/(r-rs) and 1/sin(th) are R*(r-rs)*sin, R*r*sin and R*r*(r-rs);
+//   * one sincos per flow instead of 3 sin + 1 cos;
+//   * the trailing A(d/2) of step k and the leading A(d/2) of step k+1 read the same (q1,p2)
+//     (A only writes p1,q2), so they are evaluated once and applied as A(d);
+//   * the mixed flow uses pre-halved cos/sin(2 w d) computed once on the host.
+// These change rounding at the ulp level only (the reference's own GPU build already differs
+// from its CPU simulator by FMA contraction); parity is asserted at 1e-9 relative on final
+// states and bit-exact on class / texel (tests/).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace schw {
+
+// ---------------------------------------------------------------------------------------------
+// Parameters (passed by value as __grid_constant__ kernel arguments => constant bank operands)
+// ---------------------------------------------------------------------------------------------
+struct StepParams {
+    double h;        // 0.5*delta                         (cuda_geodesic.py:571-575)
+    double delta;    // full step, used for merged A(d)
+    double rs;       // 2*mass                             (cuda_geodesic.py:635)
+    double rcap;     // 1.1*rs evaluated in FP64           (cuda_geodesic.py:598)
+    double r_max;
+    double hmc, hms; // 0.5*cos(2 w d), 0.5*sin(2 w d)     (cuda_geodesic.py:545-546)
+    int32_t steps;
+    int32_t _pad;
+};
+
+struct SceneParams {
+    // camera (raytracing.py:60-88), precomputed on the host in FP64 exactly as the reference does
+    double obs[3];
+    double pc[3];                 // plane_center
+    double plane_width, plane_height;
+    // observer in spherical coordinates and the null-momentum constants (utils.py:39-88,118,140,179)
+    double r_obs, th_obs, ph_obs;
+    double f_r;                   // sqrt(1-2M/r_obs)
+    double grr, gthth, gphph;     // f, 1/r^2, 1/(r^2 sin^2 th)
+    double m4A;                   // -4*A      (A = -1/f)
+    double twomA;                 // 2*(-A)
+    // classification (raytracing.py:166-174,205-216)
+    double rs12;                  // rs*1.2
+    double bh_angle;              // asin(3*sqrt(3)*rs/obs_x)/2
+    double r_max;
+    double theta0, theta1, phi0, phi_span;
+    double pct, pcp, half_pst, half_psp;
+    int32_t height, width;
+    int32_t flip_theta, flip_phi;
+    int32_t has_texture;
+    int32_t row_begin, row_stride, nrows;
+};
+
+struct RayState {
+    double q1t, q1r, q1h, q1p;
+    double p1t, p1r, p1h, p1p;
+    double q2t, q2r, q2h, q2p;
+    double p2t, p2r, p2h, p2p;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Reciprocal for the flow: MUFU.RCP64H seed + Newton (cubic then quadratic).  D = r (r-rs) sin th
+// is a normal, non-zero number on every ray the reference handles (it divides by the same
+// factors), so no special-case path is needed: inf/NaN/0 propagate as NaN and the ray ends as
+// 'in_domain' exactly like a NaN in the reference.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One Hamiltonian flow (A or B):  given the position (r,th) of one phase-space copy and the
+// momenta (pt,pr,ph,pp) of the other, advance the *other* momenta / positions by hh.
+//   _flow_A_dev / _flow_B_dev           cuda_geodesic.py:501-525
+//   _part_ham_flow, _metric_derivative  cuda_geodesic.py:450-487  (numerators literal 2.0)
+//   _metric_vec_mul, _metric_contravariant  cuda_geodesic.py:433-447,490-498
+// With ir=1/r, id=1/(r-rs), is=1/sin th:
+//   dH/dr  = id^2 pt^2 + ir^2 pr^2 - ir^3 pth^2 - ir^3 is^2 pph^2
+//   dH/dth = -cos(th) ir^2 is^3 pph^2
+//   g.p    = ( -r id pt, (1-rs ir) pr, ir^2 pth, ir^2 is^2 pph )
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void flow(double r, double th,
+                                     double pt, double pr, double ph, double pp,
+                                     double &Pr, double &Ph,                       // momenta updated
+                                     double &Qt, double &Qr, double &Qh, double &Qp,  // positions updated
+                                     double hh, double rs)
+{
+    double s, c;
+    sincos(th, &s, &c);
+    const double d   = r - rs;
+    const double ds  = d * s;
+    const double rsn = r * s;
+    const double rd  = r * d;
+    const double R   = fast_rcp(rd * s);
+    const double ir  = R * ds;
+    const double id  = R * rsn;
+    const double is  = R * rd;
+    const double f   = fma(-rs, ir, 1.0);
+    const double A1  = id * pt;
+    const double A2  = ir * pr;
+    const double A3  = ir * ph;
+    const double w   = ir * is;
+    const double A4  = w * pp;
+    const double k   = A4 * A4;
+    const double e   = fma(A3, A3, k);
+    double dHr = A1 * A1;
+    dHr = fma(A2, A2, dHr);
+    dHr = fma(-ir, e, dHr);
+    const double dHh = -(c * is) * k;
+    Pr = fma(-hh, dHr, Pr);
+    Ph = fma(-hh, dHh, Ph);
+    Qt = fma(-hh, r * A1, Qt);
+    Qr = fma(hh, f * pr, Qr);
+    Qh = fma(hh, ir * A3, Qh);
+    Qp = fma(hh, w * A4, Qp);
+}
+
+// _flow_mixed_dev, cuda_geodesic.py:528-566, for one component.
+__device__ __forceinline__ void mix(double &q1, double &p1, double &q2, double &p2, double hmc, double hms)
+{
+    const double qs = q1 + q2, qd = q1 - q2;
+    const double ps = p1 + p2, pd = p1 - p2;
+    const double u = fma(pd, hms, qd * hmc);
+    const double v = fma(-qd, hms, pd * hmc);
+    q1 = fma(0.5, qs, u);
+    q2 = fma(0.5, qs, -u);
+    p1 = fma(0.5, ps, v);
+    p2 = fma(0.5, ps, -v);
+}
+
+__device__ __forceinline__ void flow_A(RayState &S, double hh, double rs)
+{
+    flow(S.q1r, S.q1h, S.p2t, S.p2r, S.p2h, S.p2p, S.p1r, S.p1h, S.q2t, S.q2r, S.q2h, S.q2p, hh, rs);
+}
+__device__ __forceinline__ void flow_B(RayState &S, double hh, double rs)
+{
+    flow(S.q2r, S.q2h, S.p1t, S.p1r, S.p1h, S.p1p, S.p2r, S.p2h, S.q1t, S.q1r, S.q1h, S.q1p, hh, rs);
+}
+__device__ __forceinline__ void flow_C(RayState &S, double hmc, double hms)
+{
+    mix(S.q1t, S.p1t, S.q2t, S.p2t, hmc, hms);
+    mix(S.q1r, S.p1r, S.q2r, S.p2r, hmc, hms);
+    mix(S.q1h, S.p1h, S.q2h, S.p2h, hmc, hms);
+    mix(S.q1p, S.p1p, S.q2p, S.p2p, hmc, hms);
+}
+
+// B(d/2) C(d) B(d/2): the part of _fantasy_step_ord2 (cuda_geodesic.py:569-575) between the two
+// A half-flows.  After it q1 is final for this step (the trailing A does not touch q1).
+__device__ __forceinline__ void step_BCB(RayState &S, const StepParams &P)
+{
+    flow_B(S, P.h, P.rs);
+    flow_C(S, P.hmc, P.hms);
+    flow_B(S, P.h, P.rs);
+}
+
+// Termination test of cuda_geodesic.py:598 / :623 on copy 1, plus NaN (a NaN r never terminates
+// in the reference and ends as an all-NaN state at the step cap; we stop at once, see D-9).
+__device__ __forceinline__ bool terminated(double r, const StepParams &P)
+{
+    return (r <= P.rcap) || (r >= P.r_max);
+}
+
+__device__ __forceinline__ void init_state(RayState &S, const double q0[4], const double p0[4])
+{
+    S.q1t = S.q2t = q0[0]; S.q1r = S.q2r = q0[1]; S.q1h = S.q2h = q0[2]; S.q1p = S.q2p = q0[3];
+    S.p1t = S.p2t = p0[0]; S.p1r = S.p2r = p0[1]; S.p1h = S.p2h = p0[2]; S.p1p = S.p2p = p0[3];
+}
+
+// ---------------------------------------------------------------------------------------------
+// EinsteinPy coordinate helpers (einsteinpy.coordinates.utils, restated)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void c2s(double x, double y, double z, double &r, double &th, double &ph)
+{
+    const double hxy = hypot(x, y);
+    r = hypot(hxy, z);
+    th = atan2(hxy, z);
+    ph = atan2(y, x);
+}
+
+// Python float modulo: result takes the sign of the divisor.
+__device__ __forceinline__ double pymod(double a, double b)
+{
+    double m = fmod(a, b);
+    if (m != 0.0) { if ((m < 0.0) != (b < 0.0)) m += b; }
+    else m = copysign(0.0, b);
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stages 1+2: pixel (i,j) -> q0, p0, alpha0, beta (+ diagnostic heading)
+//   camera plane            raytracing.py:74-88
+//   get_initial_conditions  utils.py:91-141;  angles_to_p_sph :148-194;
+//   build_null_4momentum_ep_sph :39-88 (future=True)
+// ---------------------------------------------------------------------------------------------
+struct RayIC {
+    double p0[4];
+    double alpha0, beta;
+    double dir[3];     // normalised un-rotated ray (for the diagnostic h_r,h_theta,h_phi)
+};
+
+__device__ __forceinline__ void initial_conditions_px(const SceneParams &sc, double px, double py, double pz, RayIC &ic)
+{
+    double d0 = px - sc.obs[0], d1 = py - sc.obs[1], d2 = pz - sc.obs[2];
+    const double nrm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    d0 /= nrm; d1 /= nrm; d2 /= nrm;
+    const double beta = atan2(d2, d1);
+    double s, c;
+    sincos(-beta, &s, &c);
+    const double rx = d0;
+    const double ry = c * d1 - s * d2;
+    // h_phi = atan2(y', x') of the rotated ray (cartesian_to_spherical_fast, utils.py:124)
+    const double h_phi = atan2(ry, rx);
+    const double alpha = 3.141592653589793 - h_phi;
+    double sa, ca;
+    sincos(alpha, &sa, &ca);
+    const double pr  = (-ca) * sc.f_r;
+    const double pth = -0.0 * sc.r_obs;          // n_thhat = -sin(0.0)
+    const double pph = sa * sc.r_obs;
+    const double C = sc.grr * pr * pr + sc.gthth * pth * pth + sc.gphph * pph * pph;
+    const double disc = sc.m4A * C;
+    ic.p0[0] = sqrt(disc) / sc.twomA;
+    ic.p0[1] = pr; ic.p0[2] = pth; ic.p0[3] = pph;
+    ic.alpha0 = acos(-pr / sc.f_r);
+    ic.beta = beta;
+    ic.dir[0] = d0; ic.dir[1] = d1; ic.dir[2] = d2;
+}
+
+__device__ __forceinline__ void initial_conditions(const SceneParams &sc, int i, int j, RayIC &ic)
+{
+    const double u = (j + 0.5) / sc.width - 0.5;
+    const double v = (i + 0.5) / sc.height - 0.5;
+    initial_conditions_px(sc, sc.pc[0], sc.pc[1] + u * sc.plane_width, sc.pc[2] + v * sc.plane_height, ic);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 5: rotate back by +beta, classify, texel lookup   (raytracing.py:166-174,181-273)
+// ---------------------------------------------------------------------------------------------
+struct RayHit {
+    double th_hit, ph_hit;   // as written to photon_data.csv
+    int32_t u, v;            // texel or -1
+    uint8_t cls, r, g, b;
+};
+
+__device__ __forceinline__ void classify(const SceneParams &sc, const uint8_t *__restrict__ tex,
+                                         double r_bh, double th, double ph, double alpha0, double beta,
+                                         RayHit &o)
+{
+    double sph, cph, sth, cth, sb, cb;
+    sincos(ph, &sph, &cph);
+    sincos(th, &sth, &cth);
+    const double x = r_bh * cph * sth;
+    const double y = r_bh * sph * sth;
+    const double z = r_bh * cth;
+    sincos(beta, &sb, &cb);
+    const double y2 = cb * y - sb * z;
+    const double z2 = sb * y + cb * z;
+    double rr, th_hit, ph_hit;
+    c2s(x, y2, z2, rr, th_hit, ph_hit);
+    o.u = o.v = -1;
+    o.r = o.g = o.b = 0;
+    if ((r_bh <= sc.rs12) || (alpha0 <= sc.bh_angle)) {
+        o.cls = 0;
+    } else if (r_bh >= 100.0) {
+        o.cls = 1; o.r = 255;
+    } else if (r_bh >= sc.r_max) {
+        o.cls = 3;
+        if (sc.has_texture) {
+            const double two_pi = 6.283185307179586;
+            th_hit = pymod(th_hit, two_pi);
+            ph_hit = pymod(ph_hit, two_pi);
+            const double dtheta = fabs(th_hit - sc.pct);
+            if (sc.flip_phi) ph_hit = -ph_hit;
+            const double phi_rel = pymod(ph_hit - sc.phi0, two_pi);
+            const double dphi = fabs(pymod(ph_hit - sc.pcp + 3.141592653589793, two_pi) - 3.141592653589793);
+            if ((dtheta <= sc.half_pst) && (dphi <= sc.half_psp)) {
+                const double theta_map = sc.flip_theta ? (3.141592653589793 - th_hit) : th_hit;
+                const double fu = (theta_map - sc.theta0) / (sc.theta1 - sc.theta0) * (sc.height - 1) + 0.5;
+                const double fv = phi_rel / sc.phi_span * (sc.width - 1) + 0.5;
+                long long uu = (long long)fu, vv = (long long)fv;       // int(): truncation toward zero
+                uu = uu < 0 ? 0 : (uu > sc.height - 1 ? sc.height - 1 : uu);
+                vv = vv < 0 ? 0 : (vv > sc.width - 1 ? sc.width - 1 : vv);
+                const uint8_t *t = tex + ((size_t)uu * sc.width + vv) * 3;
+                o.r = __ldg(t); o.g = __ldg(t + 1); o.b = __ldg(t + 2);
+                o.u = (int32_t)uu; o.v = (int32_t)vv;
+                o.cls = 2;
+            }
+        }
+    } else {
+        o.cls = 4;
+    }
+    o.th_hit = th_hit; o.ph_hit = ph_hit;
+}
+
+}  // namespace schw

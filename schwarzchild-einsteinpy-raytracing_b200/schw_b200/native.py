@@ -1,0 +1,274 @@
+"""ctypes binding of libschw_b200.so (C ABI: include/schw_b200.h).
+
+This is the only way the Python host side reaches the GPU.  There is no CPU fallback:
+if the shared library is missing or no sm_100 device is present the calls raise.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "lib", "libschw_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+
+CLASSES = ("bh", "numerical error", "escape_bg", "escape_no_patch", "in_domain")
+
+SCHW_OK, SCHW_E_INVALID, SCHW_E_CUDA, SCHW_E_HORIZON, SCHW_E_NULLCOND, SCHW_E_RAYPLANE, SCHW_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
+
+# every symbol include/schw_b200.h declares (tests/test_abi_symbols.py checks header <-> library <-> this list)
+EXPORTS = (
+    "schw_abi_version", "schw_last_error", "schw_create", "schw_destroy", "schw_device_info",
+    "schw_last_kernel_ms", "schw_integrate_batch", "schw_integrate_batch_dev", "schw_integrate_batch_full",
+    "schw_initial_conditions", "schw_initial_conditions_px", "schw_classify", "schw_render", "schw_render_dev", "schw_last_total_steps",
+    "schw_flat_render", "schw_fp64_peak_probe",
+)
+
+
+class SchwScene(C.Structure):
+    _fields_ = [
+        ("obs", C.c_double * 3), ("fov", C.c_double),
+        ("height", C.c_int32), ("width", C.c_int32),
+        ("mass", C.c_double), ("r_max", C.c_double),
+        ("steps", C.c_int64), ("delta", C.c_double), ("omega", C.c_double),
+        ("patch_center_theta", C.c_double), ("patch_center_phi", C.c_double),
+        ("patch_size_theta", C.c_double), ("patch_size_phi", C.c_double),
+        ("flip_theta", C.c_int32), ("flip_phi", C.c_int32),
+        ("has_texture", C.c_int32), ("_pad", C.c_int32),
+    ]
+
+
+class SchwRayOutputs(C.Structure):
+    _fields_ = [("final_q", C.c_void_p), ("ic", C.c_void_p), ("hit", C.c_void_p),
+                ("texel", C.c_void_p), ("nsteps", C.c_void_p)]
+
+
+class SchwError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libschw_b200 error {code}: {msg}")
+        self.code = code
+
+
+def build(force=False):
+    """Compile libschw_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in ("schw_kernels.cu", "schw_device.cuh")]
+    srcs.append(os.path.join(os.path.dirname(_PKG), "include", "schw_b200.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", CSRC, "-s"] + (["-B"] if force else []))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and declare prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SchwError(SCHW_E_CUDA, f"{LIB_PATH} not found — run __graft_entry__.build() (no CPU fallback exists)")
+    L = C.CDLL(LIB_PATH)
+    vp, dp, i64, i32, dbl = C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double
+    scp = C.POINTER(SchwScene)
+    xop = C.POINTER(SchwRayOutputs)
+    L.schw_abi_version.restype = C.c_int
+    L.schw_last_error.restype = C.c_char_p
+    L.schw_create.argtypes = [i32, C.POINTER(vp)]
+    L.schw_destroy.argtypes = [vp]
+    L.schw_device_info.argtypes = [vp, C.c_char_p, i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.schw_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.schw_last_total_steps.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.schw_integrate_batch.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp]
+    L.schw_integrate_batch_dev.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp, vp]
+    L.schw_integrate_batch_full.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp]
+    L.schw_initial_conditions.argtypes = [vp, scp, i32, i32, i32, dp, dp]
+    L.schw_initial_conditions_px.argtypes = [vp, dp, dp, i64, dbl, dp, dp]
+    L.schw_classify.argtypes = [vp, scp, dp, dp, dp, i64, vp, vp, vp, dp, vp]
+    L.schw_render.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop]
+    L.schw_render_dev.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop, vp]
+    L.schw_flat_render.argtypes = [vp, scp, vp, vp]
+    L.schw_fp64_peak_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    for name in EXPORTS:
+        if name not in ("schw_last_error",):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load().schw_last_error().decode("utf-8", "replace")
+        if rc == SCHW_E_HORIZON:
+            raise ValueError(msg)                 # simulation/utils.py:67-68
+        if rc == SCHW_E_NULLCOND:
+            raise RuntimeError(msg)               # simulation/utils.py:80-81
+        if rc == SCHW_E_RAYPLANE:
+            raise AssertionError(msg)             # simulation/utils.py:113,126
+        if rc == SCHW_E_INVALID:
+            raise ValueError(msg)
+        raise SchwError(rc, msg)
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def make_scene(obs=(30.0, 0.0, 0.0), fov=np.radians(80.0), height=400, width=400, mass=1.0, r_max=31.0,
+               steps=200000, delta=0.01, omega=1.0, patch_center_theta=np.pi / 2, patch_center_phi=np.pi,
+               patch_size_theta=np.pi, patch_size_phi=2 * np.pi, flip_theta=False, flip_phi=False,
+               has_texture=True):
+    s = SchwScene()
+    s.obs[0], s.obs[1], s.obs[2] = [float(v) for v in obs]
+    s.fov = float(fov); s.height = int(height); s.width = int(width)
+    s.mass = float(mass); s.r_max = float(r_max); s.steps = int(steps)
+    s.delta = float(delta); s.omega = float(omega)
+    s.patch_center_theta = float(patch_center_theta); s.patch_center_phi = float(patch_center_phi)
+    s.patch_size_theta = float(patch_size_theta); s.patch_size_phi = float(patch_size_phi)
+    s.flip_theta = int(bool(flip_theta)); s.flip_phi = int(bool(flip_phi)); s.has_texture = int(bool(has_texture))
+    return s
+
+
+class Handle:
+    """One CUDA stream + scratch on one device (schw_create / schw_destroy)."""
+
+    def __init__(self, device=-1):
+        self._L = load()
+        self._h = C.c_void_p()
+        _check(self._L.schw_create(int(device), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.schw_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- info / measurement -------------------------------------------------------------------
+    def device_info(self):
+        name = C.create_string_buffer(256)
+        sm, khz = C.c_int(), C.c_int()
+        _check(self._L.schw_device_info(self._h, name, 256, C.byref(sm), C.byref(khz)))
+        return dict(name=name.value.decode(), sm_count=sm.value, clock_khz=khz.value)
+
+    def last_kernel_ms(self):
+        ms, n = C.c_float(), C.c_int()
+        _check(self._L.schw_last_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def last_total_steps(self):
+        v = C.c_uint64()
+        _check(self._L.schw_last_total_steps(self._h, C.byref(v)))
+        return int(v.value)
+
+    def fp64_peak_probe(self):
+        t, ms = C.c_double(), C.c_float()
+        _check(self._L.schw_fp64_peak_probe(self._h, C.byref(t), C.byref(ms)))
+        return t.value, ms.value
+
+    # -- integrator -----------------------------------------------------------------------------
+    def integrate_batch(self, q0s, p0s, steps, delta, rs, r_max, omega, want_steps=False):
+        q0s = np.ascontiguousarray(q0s, np.float64); p0s = np.ascontiguousarray(p0s, np.float64)
+        if q0s.ndim != 2 or q0s.shape[1] != 4 or p0s.shape != q0s.shape:
+            raise ValueError("q0s and p0s must both have shape (n, 4)")
+        n = q0s.shape[0]
+        out = np.zeros((n, 4), np.float64)
+        ns = np.zeros(n, np.int32) if want_steps else None
+        _check(self._L.schw_integrate_batch(self._h, _p(q0s), _p(p0s), n, int(steps), float(delta), float(rs),
+                                            float(r_max), float(omega), _p(out), _p(ns)))
+        return (out, ns) if want_steps else out
+
+    def integrate_batch_dev(self, d_q0s, d_p0s, n, steps, delta, rs, r_max, omega, d_out, d_steps=0, stream=0):
+        _check(self._L.schw_integrate_batch_dev(self._h, C.c_void_p(d_q0s), C.c_void_p(d_p0s), int(n), int(steps),
+                                                float(delta), float(rs), float(r_max), float(omega),
+                                                C.c_void_p(d_out), C.c_void_p(d_steps or None),
+                                                C.c_void_p(stream or None)))
+
+    def integrate_batch_full(self, q0s, p0s, steps, delta, rs, r_max, omega, want_rows=False):
+        q0s = np.ascontiguousarray(q0s, np.float64); p0s = np.ascontiguousarray(p0s, np.float64)
+        if q0s.ndim != 2 or q0s.shape[1] != 4 or p0s.shape != q0s.shape:
+            raise ValueError("q0s and p0s must both have shape (n, 4)")
+        n = q0s.shape[0]
+        traj = np.zeros((n, int(steps), 4), np.float64)        # np.zeros like cuda_geodesic.py:649
+        rows = np.zeros(n, np.int64)
+        _check(self._L.schw_integrate_batch_full(self._h, _p(q0s), _p(p0s), n, int(steps), float(delta), float(rs),
+                                                 float(r_max), float(omega), _p(traj), _p(rows)))
+        return (traj, rows) if want_rows else traj
+
+    # -- stages -----------------------------------------------------------------------------------
+    def initial_conditions(self, scene, row_begin=0, row_end=None, row_stride=1):
+        row_end = scene.height if row_end is None else row_end
+        n = len(range(row_begin, row_end, row_stride)) * scene.width
+        q0s = np.zeros((n, 4)); ic = np.zeros((n, 9))
+        _check(self._L.schw_initial_conditions(self._h, C.byref(scene), row_begin, row_end, row_stride, _p(q0s), _p(ic)))
+        return q0s, ic
+
+    def initial_conditions_px(self, obs, pixels, mass):
+        obs = np.ascontiguousarray(obs, np.float64); pixels = np.ascontiguousarray(pixels, np.float64).reshape(-1, 3)
+        n = pixels.shape[0]
+        q0s = np.zeros((n, 4)); ic = np.zeros((n, 9))
+        _check(self._L.schw_initial_conditions_px(self._h, _p(obs), _p(pixels), n, float(mass), _p(q0s), _p(ic)))
+        return q0s, ic
+
+    def classify(self, scene, final_q, alpha0, beta, tex):
+        final_q = np.ascontiguousarray(final_q, np.float64).reshape(-1, 4)
+        alpha0 = np.ascontiguousarray(alpha0, np.float64); beta = np.ascontiguousarray(beta, np.float64)
+        n = final_q.shape[0]
+        tex = None if tex is None else np.ascontiguousarray(tex, np.uint8)
+        rgb = np.zeros((n, 3), np.uint8); cls = np.zeros(n, np.uint8)
+        hit = np.zeros((n, 2)); uv = np.zeros((n, 2), np.int32)
+        _check(self._L.schw_classify(self._h, C.byref(scene), _p(final_q), _p(alpha0), _p(beta), n, _p(tex),
+                                     _p(rgb), _p(cls), _p(hit), _p(uv)))
+        return dict(rgb=rgb, cls=cls, hit=hit, uv=uv)
+
+    # -- fused render -----------------------------------------------------------------------------
+    def render(self, scene, tex, row_begin=0, row_end=None, row_stride=1, extras=False):
+        """Host-buffer render (H2D of the texture and D2H of the outputs happen inside the call)."""
+        row_end = scene.height if row_end is None else row_end
+        nrows = len(range(row_begin, row_end, row_stride))
+        w = scene.width
+        n = nrows * w
+        tex = None if tex is None else np.ascontiguousarray(tex, np.uint8)
+        if tex is not None and tex.shape != (scene.height, scene.width, 3):
+            raise ValueError("texture must be (height, width, 3) uint8 (the sky resized to the frame)")
+        rgb = np.zeros((nrows, w, 3), np.uint8); cls = np.zeros((nrows, w), np.uint8)
+        out = dict(rgb=rgb, cls=cls)
+        x = None
+        if extras:
+            out.update(final_q=np.zeros((n, 4)), ic=np.zeros((n, 9)), hit=np.zeros((n, 2)),
+                       uv=np.zeros((n, 2), np.int32), nsteps=np.zeros(n, np.int32))
+            x = SchwRayOutputs(out["final_q"].ctypes.data, out["ic"].ctypes.data, out["hit"].ctypes.data,
+                               out["uv"].ctypes.data, out["nsteps"].ctypes.data)
+        _check(self._L.schw_render(self._h, C.byref(scene), _p(tex), row_begin, row_end, row_stride,
+                                   _p(rgb), _p(cls), C.byref(x) if x is not None else None))
+        return out
+
+    def render_dev(self, scene, d_tex, row_begin, row_end, row_stride, d_rgb, d_cls, stream=0,
+                   d_final_q=0, d_ic=0, d_hit=0, d_texel=0, d_nsteps=0):
+        """Device-pointer render: enqueue only (pointers are e.g. torch tensors' data_ptr())."""
+        x = SchwRayOutputs(d_final_q or None, d_ic or None, d_hit or None, d_texel or None, d_nsteps or None)
+        _check(self._L.schw_render_dev(self._h, C.byref(scene), C.c_void_p(d_tex or None), row_begin, row_end,
+                                       row_stride, C.c_void_p(d_rgb), C.c_void_p(d_cls), C.byref(x),
+                                       C.c_void_p(stream or None)))
+
+    def flat_render(self, scene, tex):
+        tex = np.ascontiguousarray(tex, np.uint8)
+        rgb = np.zeros((scene.height, scene.width, 3), np.uint8)
+        _check(self._L.schw_flat_render(self._h, C.byref(scene), _p(tex), _p(rgb)))
+        return rgb
+
+
+_default = {}
+
+
+def default_handle(device=-1):
+    """Process-wide handle per device (created on first use)."""
+    if device not in _default:
+        _default[device] = Handle(device)
+    return _default[device]

@@ -1,0 +1,141 @@
+"""Curved-space render with the reference's entry point (simulation/raytracing.py:16-314).
+
+`run_manual_simulation` keeps the reference's signature, return value, side effects
+(images/manual_output.png, photon_data.csv, sampled_rays.csv, printed summary) and quirks
+(SURVEY.md App. D), but the O(h*w) Python loops of the reference — camera rays (:83-88),
+initial conditions (:108-116), integration (:118-120) and classification / texture lookup
+(:179-273) — are ONE fused sm_100a kernel launch (schw_render).  Under torchrun
+(WORLD_SIZE > 1) the pixel rows are sharded row-cyclically over the ranks and gathered with one
+NCCL all_gather (schw_b200.multigpu).
+"""
+import logging
+import os
+
+import numpy as np
+from PIL import Image
+
+from schw_b200 import CLASSES, default_handle, make_scene
+from simulation.utils import spherical_to_cartesian_fast, cartesian_to_spherical_fast  # noqa: F401  (re-exported like the reference, raytracing.py:13)
+
+MAX_POINTS = 1000            # cap of stored points per sampled ray (raytracing.py:124)
+
+
+def _load_texture(background_path, h, w):
+    """Sky resized to the FRAME size with PIL LANCZOS, exactly the reference's call (raytracing.py:36-37)."""
+    if background_path is None:
+        return None
+    return np.array(Image.open(background_path).convert('RGB').resize((w, h), Image.LANCZOS))
+
+
+def _save_png(path, img):
+    os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
+    try:
+        import matplotlib.pyplot as plt      # the reference saves through plt.imsave (raytracing.py:282)
+        plt.imsave(path, img)
+    except ImportError:
+        Image.fromarray(img).save(path)
+
+
+def scene_from_args(bh, observer, steps, delta, boundary_radius, patch_center_theta, patch_center_phi,
+                    patch_size_theta, patch_size_phi, flip_theta, flip_phi, has_texture):
+    h, w = observer.image_size
+    # omega: run_manual_simulation never forwards its omega argument (raytracing.py:118), so the
+    # integrator default 1.0 (cuda_geodesic.py:632) is what the reference actually integrates with.
+    return make_scene(obs=np.asarray(observer.position, np.float64), fov=float(observer.fov), height=h, width=w,
+                      mass=float(bh.mass), r_max=float(boundary_radius), steps=int(steps), delta=float(delta),
+                      omega=1.0, patch_center_theta=patch_center_theta, patch_center_phi=patch_center_phi,
+                      patch_size_theta=patch_size_theta, patch_size_phi=patch_size_phi,
+                      flip_theta=flip_theta, flip_phi=flip_phi, has_texture=has_texture)
+
+
+def run_manual_simulation(
+    bh, observer, real_time=False, update_every=32,
+    steps=500, delta=0.2, omega=1.0, rtol=1e-2, atol=1e-2, order=2, suppress_warnings=False,
+    background_path=None, use_cuda=False,
+    boundary_radius=None,
+    patch_center_theta=np.pi/2, patch_center_phi=np.pi, patch_size_theta=np.deg2rad(10), patch_size_phi=np.deg2rad(10),
+    flip_theta=False, flip_phi=False,
+    n_samples=0,
+    write_outputs=True,
+):
+    """Render the lensed image; returns `img` (h,w,3) uint8, or `(img, sampled_trajectories)` when n_samples > 0.
+
+    `real_time, update_every, omega, rtol, atol, order, suppress_warnings` are accepted and ignored,
+    as in the reference.  `write_outputs=False` (additive) skips the PNG/CSV side effects.
+    """
+    logging.info("Starting manual ray tracing simulation...")
+    h, w = observer.image_size
+    if not use_cuda:
+        # reference: the CPU branch is `pass` and crashes with NameError at raytracing.py:131
+        raise RuntimeError("run_manual_simulation: only the CUDA path exists (use_cuda=True); there is no CPU fallback")
+    if boundary_radius is None:
+        raise TypeError("boundary_radius must be given (the reference passes it to the integrator as r_max)")
+    bg_array = _load_texture(background_path, h, w)
+    img = np.zeros((h, w, 3), dtype=np.uint8)
+
+    sampled_indices = set()
+    if n_samples > 0:
+        import random
+        while len(sampled_indices) < n_samples:           # unseeded draw like raytracing.py:44-48
+            sampled_indices.add((random.randint(0, h - 1), random.randint(0, w - 1)))
+    if not (n_samples > 0 and sampled_indices):
+        # reference quirk (App. D-3): the whole image-building block is nested under this test
+        print("Summary counts not available (CPU fallback mode).")
+        return img
+
+    scene = scene_from_args(bh, observer, steps, delta, boundary_radius, patch_center_theta, patch_center_phi,
+                            patch_size_theta, patch_size_phi, flip_theta, flip_phi, bg_array is not None)
+    logging.info("Using CUDA Schwarzschild integrator for curved rays ...")
+    from schw_b200.multigpu import render_frame
+    out = render_frame(scene, bg_array, extras=True)
+    img = out["rgb"]
+    cls = out["cls"].reshape(-1)
+    ic = out["ic"]
+    betas = ic[:, 5]
+
+    # ── sampled trajectories (raytracing.py:126-159): full integration of the sampled pixels ──────────
+    print("Handling sample trajectories (CUDA)...")
+    sample_flat_idx = np.array([i * w + j for (i, j) in sampled_indices], dtype=np.int64)
+    q0 = np.tile(out["q0"], (len(sample_flat_idx), 1))
+    traj_out = default_handle().integrate_batch_full(q0, ic[sample_flat_idx, 0:4], steps, delta, 2.0 * bh.mass,
+                                                     boundary_radius, 1.0)
+    n_steps_full = traj_out.shape[1]
+    keep_idx = np.linspace(0, n_steps_full - 1, num=min(MAX_POINTS, n_steps_full), dtype=np.int32)
+    sampled_traj_data = []
+    for s, flat in enumerate(sample_flat_idx):
+        r, th, ph = traj_out[s, keep_idx, 1], traj_out[s, keep_idx, 2], traj_out[s, keep_idx, 3]
+        x = r * np.cos(ph) * np.sin(th)
+        y = r * np.sin(ph) * np.sin(th)
+        z = r * np.cos(th)
+        c, sn = np.cos(betas[flat]), np.sin(betas[flat])
+        sampled_traj_data.append(np.stack([x, c * y - sn * z, sn * y + c * z], axis=1).astype(np.float64))
+
+    if write_outputs:
+        import pandas as pd
+        _save_png('images/manual_output.png', img)
+        logging.info("Saved manual_output.png")
+        print("Saving ray photon data...")
+        ii, jj = np.divmod(np.arange(h * w), w)
+        pd.DataFrame({
+            'i': ii, 'j': jj,
+            'final_r': out["final_q"][:, 1], 'final_th': out["hit"][:, 0], 'final_ph': out["hit"][:, 1],
+            'collision': np.array(CLASSES, dtype=object)[cls],
+            'h_r': ic[:, 6], 'h_theta': ic[:, 7], 'h_phi': ic[:, 8],
+            'p0_t': ic[:, 0], 'p0_r': ic[:, 1], 'p0_th': ic[:, 2], 'p0_ph': ic[:, 3],
+            'alpha0': ic[:, 4],
+        }).to_csv('photon_data.csv', index=False)
+        print("Saving diagnostic sampled trajectories ...")
+        frames = []
+        for ridx, traj in enumerate(sampled_traj_data):
+            # quirk App. D-7: the heading columns are indexed by SAMPLE number, not by pixel (raytracing.py:296)
+            frames.append(pd.DataFrame({
+                'ray_id': ridx, 'point_idx': np.arange(len(traj)), 'x': traj[:, 0], 'y': traj[:, 1], 'z': traj[:, 2],
+                'r': np.sqrt(traj[:, 0] ** 2 + traj[:, 1] ** 2 + traj[:, 2] ** 2),
+                'h_r': ic[ridx, 6], 'h_theta': ic[ridx, 7], 'h_phi': ic[ridx, 8]}))
+        pd.concat(frames).to_csv('sampled_rays.csv', index=False)
+
+    n_captured = int(np.sum(cls == 0))
+    n_escaped = int(np.sum(cls == 3))
+    n_bg = int(np.sum(cls == 2))
+    print(f"Summary: {n_captured} rays captured by BH, {n_escaped} rays escaped, {n_bg} rays hit the background image.")
+    return img, sampled_traj_data

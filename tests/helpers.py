@@ -1,0 +1,87 @@
+"""Shared helpers for the parity tests (bands of SURVEY §8c, scene builders, texel boundary test)."""
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# ---- stated parity bands -------------------------------------------------------------
+BAND_G = 1e-3        # grazing band: |b/(3*sqrt(3) M) - 1| < 1e-3 is excluded from state parity
+BAND_H_RMIN = 2.5    # horizon blow-up band: rays whose trajectory reaches r < 2.5 M(=1) are excluded
+STATE_RTOL = 1e-9    # north_star: final photon positions within 1e-9 relative in FP64
+
+
+def impact_parameter(p0):
+    """Reference convention b = p_phi/|p_t|."""
+    p0 = np.asarray(p0)
+    return np.abs(p0[..., 3]) / np.abs(p0[..., 0])
+
+
+def in_band_g(p0, mass=1.0):
+    return np.abs(impact_parameter(p0) / (3 * np.sqrt(3) * mass) - 1.0) < BAND_G
+
+
+def state_close(a, b, rtol=STATE_RTOL):
+    """|a-b| <= rtol*max(|b|, 1): relative on r, t, phi; absolute floor for angles near 0."""
+    a = np.asarray(a); b = np.asarray(b)
+    return np.abs(a - b) <= rtol * np.maximum(np.abs(b), 1.0)
+
+
+def scene_kwargs_from_cfg(cfg, patch_center):
+    c = json.loads(str(cfg))
+    return dict(obs=(float(c["obs_x"]), 0.0, 0.0), fov=np.radians(c["fov"]), height=c["h"], width=c["w"],
+                mass=c["mass"], r_max=float(c["r_max"]), steps=c["steps"], delta=c["delta"], omega=1.0,
+                patch_center_theta=float(patch_center[0]), patch_center_phi=float(patch_center[1]),
+                patch_size_theta=np.deg2rad(c["pst"]), patch_size_phi=np.deg2rad(c["psp"]),
+                flip_theta=c["flt"], flip_phi=c["flp"], has_texture=True), c
+
+
+def texel_coords(scene_kw, th_hit, ph_hit):
+    """Continuous texel coordinates (before int()) from the CSV hit angles (raytracing.py:229-243)."""
+    k = scene_kw
+    h, w = k["height"], k["width"]
+    theta0 = k["patch_center_theta"] - k["patch_size_theta"] / 2
+    theta1 = k["patch_center_theta"] + k["patch_size_theta"] / 2
+    phi0 = k["patch_center_phi"] - k["patch_size_phi"] / 2
+    theta_map = (np.pi - th_hit) if k["flip_theta"] else th_hit
+    fu = (theta_map - theta0) / (theta1 - theta0) * (h - 1) + 0.5
+    fv = ((ph_hit - phi0) % (2 * np.pi)) / k["patch_size_phi"] * (w - 1) + 0.5
+    return fu, fv
+
+
+def near_rounding_boundary(fu, fv, eps=1e-6):
+    return (np.abs(fu - np.round(fu)) < eps) | (np.abs(fv - np.round(fv)) < eps)
+
+
+def synthetic_sky(h, w, seed=0):
+    """Deterministic (h,w,3) uint8 texture already at frame size (stands in for the PIL-resized sky)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    t = np.empty((h, w, 3), np.uint8)
+    t[..., 0] = (xx * 255 // max(w - 1, 1)).astype(np.uint8)
+    t[..., 1] = (yy * 255 // max(h - 1, 1)).astype(np.uint8)
+    t[..., 2] = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    return t
+
+
+def random_rays(n, seed, equatorial_frac=0.5):
+    """Seeded null rays: camera-like equatorial rays and general tilted rays (like make_golden.part_stepper_general)."""
+    rng = np.random.default_rng(seed)
+    q0s = np.zeros((n, 4)); p0s = np.zeros((n, 4))
+    for k in range(n):
+        eq = rng.random() < equatorial_frac
+        r0 = rng.uniform(8.0, 40.0)
+        th0 = np.pi / 2 if eq else rng.uniform(0.35, np.pi - 0.35)
+        ph0 = rng.uniform(-np.pi, np.pi)
+        a = np.deg2rad(rng.uniform(0.0, 55.0)); b = 0.0 if eq else rng.uniform(-np.pi, np.pi)
+        pr = -np.cos(a) * np.sqrt(1 - 2 / r0)
+        pth = np.sin(a) * np.sin(b) * r0
+        pph = np.sin(a) * np.cos(b) * r0 * np.sin(th0)
+        f = 1 - 2 / r0
+        C = f * pr * pr + pth * pth / r0 ** 2 + pph * pph / (r0 * r0 * np.sin(th0) ** 2)
+        pt = np.sqrt(4 * C / f) / (2 / f)
+        q0s[k] = [0.0, r0, th0, ph0]
+        p0s[k] = [pt if k % 2 else -pt, pr, pth, pph]
+    return q0s, p0s

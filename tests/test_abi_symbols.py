@@ -1,0 +1,80 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads, and exports every symbol that
+include/schw_b200.h declares (no compute calls: there is no GPU here); the product never touches oracle/."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import PKG, ROOT
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "schw_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(schw_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import schw_b200
+    schw_b200.build()
+    lib = schw_b200.load()
+    names = _header_functions()
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/schw_b200.h but not exported"
+    assert sorted(schw_b200.EXPORTS) == names
+    nm = subprocess.check_output(["nm", "-D", "--defined-only", schw_b200.native.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (schw_\w+)", nm))
+    assert exported == set(names), exported ^ set(names)
+    assert lib.schw_abi_version() == 1
+
+
+def test_scene_struct_layout_matches_header():
+    import schw_b200
+    # 3+1 doubles, 2 int32, 2 doubles, int64, 2 doubles, 4 doubles, 4 int32  (include/schw_b200.h: schw_scene)
+    assert ctypes.sizeof(schw_b200.SchwScene) == 8 * 4 + 8 + 16 + 8 + 16 + 32 + 16 == 128
+    assert ctypes.sizeof(schw_b200.SchwRayOutputs) == 5 * 8
+    from oracle import oracle as O
+    assert ctypes.sizeof(O.OrcScene) == ctypes.sizeof(schw_b200.SchwScene)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    """Without a usable sm_100 device every entry point must fail (SCHW_E_CUDA): no CPU fallback exists."""
+    import schw_b200
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except ImportError:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present; the failure path is exercised in the CPU container")
+    with pytest.raises(schw_b200.SchwError) as e:
+        schw_b200.Handle()
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    from simulation.cuda_geodesic import CUDASchwarzschildIntegrator
+    import numpy as np
+    with pytest.raises(schw_b200.SchwError):
+        CUDASchwarzschildIntegrator(steps=5).integrate_batch(np.zeros((1, 4)), np.zeros((1, 4)))
+
+
+def test_product_never_references_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package directory may import, link or call it."""
+    bad = []
+    for dp, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                if re.search(r"\boracle\b|schw_oracle|orc_", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+    hdr = open(os.path.join(ROOT, "include", "schw_b200.h")).read()
+    assert "oracle" not in hdr
+
+
+def test_header_cites_reference_interfaces():
+    hdr = open(os.path.join(ROOT, "include", "schw_b200.h")).read()
+    for cite in ("cuda_geodesic.py:639-645", "cuda_geodesic.py:647-653", "raytracing.py:60-88", "utils.py:91-141",
+                 "raytracing.py:166-174,181-273", "background.py"):
+        assert cite in hdr, cite

@@ -1,0 +1,308 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI (schw_b200.Handle ->
+libschw_b200.so), against the CPU oracle on the same seeded inputs and against the committed
+golden fixtures made from the reference itself.
+
+Bars (north_star / SURVEY §8c):
+  * class (captured / escaped / ...) and integer texel indices: bit-exact, except rays inside the
+    stated bands — G: |b/(3 sqrt3 M) - 1| < 1e-3 (grazing), H: trajectory reaches r < 2.5 (horizon
+    blow-up, rounding-chaotic in the reference itself) — and texels whose continuous coordinate sits
+    within 1e-6 of a rounding boundary;
+  * final photon positions: 1e-9 relative (FP64) outside the bands;
+  * single-ray trajectories: 1e-9 relative per stored step.
+"""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from helpers import (STATE_RTOL, in_band_g, near_rounding_boundary, random_rays, scene_kwargs_from_cfg,
+                     state_close, synthetic_sky, texel_coords)
+
+pytestmark = pytest.mark.gpu
+
+
+COND_MAX = 1e-11     # rays whose REFERENCE result moves by more than this under a 1-ulp input change are ill-conditioned
+
+
+def _well_posed(orc, q0s, p0s, steps, delta, rs, r_max, omega):
+    """Rays on which the 1e-9 state bar applies: outside band G (grazing), outside band H (closest approach
+    of either phase-space copy >= 2.5, oracle bookkeeping) and well-conditioned in the reference's own arithmetic."""
+    _, _, rmin = orc.integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega, want_rmin=True)
+    cond = orc.conditioning(q0s, p0s, steps, delta, rs, r_max, omega)
+    return ~in_band_g(p0s) & (rmin >= 2.5) & (cond <= COND_MAX)
+
+
+# ---------------------------------------------------------------------------------------------------
+# stage 3+4: integrator
+# ---------------------------------------------------------------------------------------------------
+def test_integrate_batch_default_scene_vs_reference_golden(handle, orc, golden):
+    g = golden("stepper_default.npz")
+    steps, delta, r_max, omega = int(g["steps"]), float(g["delta"]), float(g["r_max"]), float(g["omega"])
+    out, ns = handle.integrate_batch(g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega, want_steps=True)
+    _, ns_ref = orc.integrate_batch(g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega)
+    ok = _well_posed(orc, g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega)
+    assert ok.sum() >= 17
+    assert np.array_equal(ns[ok], ns_ref[ok])                                  # same termination step
+    assert state_close(out[ok], g["out_qs"][ok]).all(), relerr(out[ok], g["out_qs"][ok], 1.0).max()
+    # band-H rays: captured/escaped side must still agree in the render (alpha0 mask), not asserted here
+
+
+def test_integrate_batch_general_rays_vs_reference_golden(handle, orc, golden):
+    g = golden("stepper_general.npz")
+    steps, delta, r_max = int(g["steps"]), float(g["delta"]), float(g["r_max"])
+    for tag, omega in (("out_w1", 1.0), ("out_w001", 0.01)):
+        out = handle.integrate_batch(g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega)
+        ok = _well_posed(orc, g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega)
+        assert ok.sum() > 80, ok.sum()
+        assert state_close(out[ok], g[tag][ok]).all(), (tag, relerr(out[ok], g[tag][ok], 1.0).max())
+
+
+def test_integrate_batch_random_rays_vs_oracle(handle, orc):
+    q0s, p0s = random_rays(4096, seed=11)
+    steps, delta, rs, r_max, omega = 4000, 0.02, 2.0, 45.0, 1.0
+    out, ns = handle.integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega, want_steps=True)
+    ref, ns_ref = orc.integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega)
+    ok = _well_posed(orc, q0s, p0s, steps, delta, rs, r_max, omega)
+    assert ok.sum() > 2000, ok.sum()
+    assert np.array_equal(ns[ok], ns_ref[ok])
+    assert state_close(out[ok], ref[ok]).all(), relerr(out[ok], ref[ok], 1.0).max()
+    # captured/escaped side agrees for every ray outside the grazing band, ill-conditioned or not
+    side = lambda r: np.where(r <= 1.1 * rs, 0, np.where(r >= r_max, 1, 2))
+    far = np.abs(np.abs(p0s[:, 3] / p0s[:, 0]) / (3 * np.sqrt(3)) - 1) > 0.05
+    assert np.mean(side(out[far, 1]) == side(ref[far, 1])) > 0.995
+
+
+def test_integrate_batch_edge_cases(handle, orc):
+    # empty batch
+    out = handle.integrate_batch(np.zeros((0, 4)), np.zeros((0, 4)), 10, 0.1, 2.0, 31.0, 1.0)
+    assert out.shape == (0, 4)
+    q0s, p0s = random_rays(37, seed=3)                 # ragged: not a multiple of the warp size
+    # steps = 0: output is q0 (cuda_geodesic.py:596-602)
+    out = handle.integrate_batch(q0s, p0s, 0, 0.1, 2.0, 100.0, 1.0)
+    assert np.array_equal(out, q0s)
+    # rays that start outside [1.1 rs, r_max): terminated before the first step
+    out, ns = handle.integrate_batch(q0s, p0s, 50, 0.1, 2.0, 5.0, 1.0, want_steps=True)
+    assert np.array_equal(out, q0s) and not ns.any()
+    # step cap reached by everyone: in-flight state equals the oracle's
+    out, ns = handle.integrate_batch(q0s, p0s, 25, 0.05, 2.0, 1e6, 0.01, want_steps=True)
+    ref, ns_ref = orc.integrate_batch(q0s, p0s, 25, 0.05, 2.0, 1e6, 0.01)
+    assert (ns == 25).all() and (ns_ref == 25).all()
+    assert relerr(out, ref, 1.0).max() < 1e-13
+    # NaN input never terminates in the reference (App. D-9): all-NaN output, no hang
+    q = q0s.copy(); q[5, 1] = np.nan
+    out = handle.integrate_batch(q, p0s, 1000, 0.05, 2.0, 45.0, 1.0)
+    assert np.isnan(out[5]).all() and np.isfinite(out[4]).all()
+    with pytest.raises(ValueError):
+        handle.integrate_batch(np.zeros((3, 3)), np.zeros((3, 3)), 1, 0.1, 2.0, 3.0, 1.0)
+
+
+def test_single_ray_trajectory_k3(handle, golden):
+    """BASELINE config 2: single_ray_cuda_test.py parameters, per-step state match."""
+    k = golden("single_ray_k3.npz")
+    traj, rows = handle.integrate_batch_full(k["q0"][None], k["p0"][None], int(k["steps"]), float(k["delta"]), 2.0,
+                                             float(k["r_max"]), float(k["omega"]), want_rows=True)
+    assert traj.shape == (1, 200000, 4)
+    n = k["traj"].shape[0]
+    assert rows[0] == n == 6665
+    assert abs(int(rows[0]) - n) <= 2 and n == 6665
+    # This omega=0.01 trajectory is exponentially unstable in the reference's own arithmetic: a 1-ulp change
+    # of p0 moves the reference's state by 2e-12 at step 3000, 8e-9 at 5000, 3e-7 at 6600 and 4e-6 at 6660
+    # (tests/test_oracle_golden.py::test_k3_conditioning).  Per-step bar: 1e-9 while the conditioning allows
+    # it, then 1000x the measured 1-ulp sensitivity.
+    assert state_close(traj[0, :2500], k["traj"][:2500]).all(), relerr(traj[0, :2500], k["traj"][:2500], 1.0).max()
+    assert state_close(traj[0, 2500:4500], k["traj"][2500:4500], 1e-7).all()
+    assert state_close(traj[0, 4500:6600], k["traj"][4500:6600], 1e-3).all()
+    assert not traj[0, rows[0]:].any()                 # zero rows after termination
+
+
+def test_trajectories_vs_einsteinpy_kats(handle, golden):
+    from test_oracle_golden import _null_pt
+    k = golden("kat_k1_einsteinpy_trajectory.npz")
+    q0 = k["q0"]; p0 = np.array([_null_pt(q0, k["p_sph"]), *k["p_sph"]])
+    traj = handle.integrate_batch_full(q0[None], p0[None], 2900, float(k["delta"]), 2.0, 1e6, float(k["omega"]))
+    T = traj[0][k["step"]]
+    xyz = np.stack([T[:, 1] * np.cos(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.sin(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.cos(T[:, 2])], 1)
+    sel = k["step"] < 2700                            # the tail of K1 runs into the horizon blow-up
+    assert relerr(T[sel, 0], k["vals"][sel, 0]).max() < 1e-9
+    assert (np.abs(xyz[sel] - k["vals"][sel, 1:4]) <= 1e-9 * np.maximum(np.abs(k["vals"][sel, 1:4]), 1.0)).all()
+    k2 = golden("kat_k2_einsteinpy_notebook.npz")
+    q0 = k2["q0"]; p0 = np.array([_null_pt(q0, k2["p_sph"]), *k2["p_sph"]])
+    traj = handle.integrate_batch_full(q0[None], p0[None], 10001, float(k2["delta"]), 2.0, 1e6, float(k2["omega"]))
+    T = traj[0][k2["step"]]
+    xyz = np.stack([T[:, 1] * np.cos(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.sin(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.cos(T[:, 2])], 1)
+    assert (np.abs(xyz - k2["xyz"]) <= 1e-9 * np.maximum(np.abs(k2["xyz"]), 1.0)).all()
+
+
+def test_integrate_batch_full_many_rays_vs_oracle(handle, orc):
+    q0s, p0s = random_rays(70, seed=5)
+    steps, delta, rs, r_max, omega = 600, 0.1, 2.0, 45.0, 1.0
+    traj, rows = handle.integrate_batch_full(q0s, p0s, steps, delta, rs, r_max, omega, want_rows=True)
+    ref, rows_ref = orc.integrate_batch_full(q0s, p0s, steps, delta, rs, r_max, omega)
+    ok = _well_posed(orc, q0s, p0s, steps, delta, rs, r_max, omega)
+    assert ok.sum() > 30, ok.sum()
+    assert np.array_equal(rows[ok], rows_ref[ok])
+    assert state_close(traj[ok], ref[ok]).all()
+    for k in np.nonzero(ok)[0]:
+        assert not traj[k, rows[k]:].any()
+
+
+# ---------------------------------------------------------------------------------------------------
+# stages 1+2 and 5
+# ---------------------------------------------------------------------------------------------------
+def test_initial_conditions_vs_reference_golden_and_oracle(handle, orc, golden):
+    import schw_b200
+    g = golden("ic_golden.npz")["table"]
+    for key in np.unique(g[:, :5], axis=0):
+        sel = np.all(g[:, :5] == key, axis=1)
+        obs_x, fov, h, w, mass = key
+        q0s, ic = handle.initial_conditions_px(np.array([obs_x, 0.0, 0.0]), g[sel][:, 20:23], mass)
+        ref = np.concatenate([g[sel][:, 11:15], g[sel][:, 15:16], g[sel][:, 19:20], g[sel][:, 16:19]], axis=1)
+        assert np.array_equal(q0s, g[sel][:, 7:11])
+        assert relerr(ic, ref, floor=1.0).max() < 1e-14
+    # whole-frame variant (pixel positions generated on the device) vs the oracle
+    sc = schw_b200.make_scene(height=24, width=36)
+    q0s, ic = handle.initial_conditions(sc)
+    osc = orc.make_scene(height=24, width=36)
+    ij = np.array([(i, j) for i in range(24) for j in range(36)], np.int32)
+    q0r, icr, rc = orc.initial_conditions((30.0, 0, 0), orc.camera_pixels(osc, ij), 1.0)
+    assert np.array_equal(q0s, q0r) and relerr(ic, icr, 1.0).max() < 1e-14
+    # strided rows (the multi-GPU sharding pattern)
+    q0s2, ic2 = handle.initial_conditions(sc, 1, 24, 3)
+    rows = np.arange(1, 24, 3)
+    assert np.array_equal(ic2.reshape(len(rows), 36, 9), ic.reshape(24, 36, 9)[rows])
+    with pytest.raises(ValueError):                     # observer inside the horizon (utils.py:67-68)
+        handle.initial_conditions(schw_b200.make_scene(obs=(1.5, 0, 0), height=4, width=4))
+
+
+def test_classify_bit_exact_vs_oracle(handle, orc):
+    import schw_b200
+    rng = np.random.default_rng(8)
+    n = 20000
+    h, w = 96, 160
+    tex = synthetic_sky(h, w, 2)
+    fq = np.zeros((n, 4))
+    fq[:, 1] = rng.choice([2.1, 2.3, 2.45, 10.0, 31.004, 33.0, 99.0, 150.0, np.nan], size=n)
+    fq[:, 2] = rng.uniform(0.0, np.pi, n)
+    fq[:, 2][rng.random(n) < 0.3] = np.pi / 2
+    fq[:, 3] = rng.uniform(-25.0, 25.0, n)
+    alpha0 = rng.uniform(0.0, 0.9, n)
+    beta = rng.uniform(-np.pi, np.pi, n)
+    for kw in (dict(), dict(flip_theta=True, flip_phi=True, patch_size_theta=np.deg2rad(70), patch_size_phi=np.deg2rad(110),
+                            patch_center_theta=np.deg2rad(100), patch_center_phi=np.deg2rad(155)),
+               dict(patch_center_phi=np.deg2rad(300), patch_size_phi=np.deg2rad(224), patch_size_theta=np.deg2rad(126))):
+        a = handle.classify(schw_b200.make_scene(height=h, width=w, **kw), fq, alpha0, beta, tex)
+        b = orc.classify(orc.make_scene(height=h, width=w, **kw), fq, alpha0, beta, tex)
+        assert np.array_equal(a["cls"], b["cls"])
+        assert set(np.unique(b["cls"])) >= {0, 1, 2, 4}
+        bad = np.any(a["uv"] != b["uv"], axis=1)
+        # device atan2/sincos are within 1-2 ulp of glibc: a texel may differ only on a rounding boundary
+        assert bad.mean() < 1e-3
+        assert np.array_equal(a["rgb"][~bad], b["rgb"][~bad])
+        fin = np.isfinite(b["hit"]).all(1)
+        assert np.abs(a["hit"][fin] - b["hit"][fin]).max() < 1e-12
+    # no texture: escape -> escape_no_patch (raytracing.py:265-268)
+    a = handle.classify(schw_b200.make_scene(height=h, width=w, has_texture=False), fq, alpha0, beta, None)
+    b = orc.classify(orc.make_scene(height=h, width=w, has_texture=False), fq, alpha0, beta, None)
+    assert np.array_equal(a["cls"], b["cls"]) and 2 not in a["cls"] and not a["rgb"][a["cls"] == 3].any()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the fused path
+# ---------------------------------------------------------------------------------------------------
+def _compare_render(kw, got, ref_cls, ref_img, ref_final_r, ref_hit, ref_alpha0, ref_p0):
+    h, w = kw["height"], kw["width"]
+    assert np.array_equal(got["cls"], ref_cls.reshape(h, w)), np.argwhere(got["cls"] != ref_cls.reshape(h, w))[:5]
+    esc = ref_cls.reshape(-1) == 2
+    fu, fv = texel_coords(kw, ref_hit[:, 0], ref_hit[:, 1])
+    diff = np.any(got["rgb"].reshape(-1, 3) != ref_img.reshape(-1, 3), axis=1)
+    assert np.all(near_rounding_boundary(fu, fv)[diff]), "image differs away from a texel rounding boundary"
+    assert diff.mean() < 5e-3
+    nb = (ref_cls.reshape(-1) != 0) & ~in_band_g(ref_p0)          # outside the bh mask (band H lives inside it) and band G
+    assert state_close(got["final_q"][nb, 1], ref_final_r[nb]).all(), relerr(got["final_q"][nb, 1], ref_final_r[nb]).max()
+    assert np.abs(got["hit"][nb & esc] - ref_hit[nb & esc]).max() < 1e-9
+    assert relerr(got["ic"][:, 4], ref_alpha0, 1.0).max() < 1e-14
+
+
+@pytest.mark.parametrize("name", ["R1", "R2", "R3", "R4", "R5"])
+def test_render_vs_reference_golden(handle, golden, name):
+    """Fused kernel against the reference's own run_manual_simulation output (class mask bit-for-bit)."""
+    import schw_b200
+    g = golden(f"render_{name}.npz")
+    kw, c = scene_kwargs_from_cfg(g["cfg"], g["patch_center"])
+    got = handle.render(schw_b200.make_scene(**kw), g["bg_array"], extras=True)
+    _compare_render(kw, got, g["cls"], g["img"], g["final_r"], np.stack([g["final_th"], g["final_ph"]], 1), g["alpha0"], g["p0"])
+
+
+def test_render_400x400_default_scene_vs_oracle(handle, orc):
+    """BASELINE config 1 (400x400, default config.py parameters) in full against the oracle."""
+    import schw_b200
+    h = w = 400
+    tex = synthetic_sky(h, w, 1)
+    got = handle.render(schw_b200.make_scene(height=h, width=w), tex, extras=True)
+    ref = orc.render(orc.make_scene(height=h, width=w), tex)
+    _compare_render(dict(height=h, width=w, patch_center_theta=np.pi / 2, patch_center_phi=np.pi, patch_size_theta=np.pi,
+                         patch_size_phi=2 * np.pi, flip_theta=False, flip_phi=False),
+                    got, ref["cls"], ref["rgb"], ref["final_q"][:, 1], ref["hit"], ref["ic"][:, 4], ref["ic"][:, 0:4])
+    # texel indices: bit-exact away from rounding boundaries, and the step counts of all non-band rays agree
+    fu, fv = texel_coords(dict(height=h, width=w, patch_center_theta=np.pi / 2, patch_center_phi=np.pi, patch_size_theta=np.pi,
+                               patch_size_phi=2 * np.pi, flip_theta=False), ref["hit"][:, 0], ref["hit"][:, 1])
+    bad = np.any(got["uv"] != ref["uv"], axis=1)
+    assert np.all(near_rounding_boundary(fu, fv)[bad])
+    nb = (ref["cls"].reshape(-1) != 0) & ~in_band_g(ref["ic"][:, 0:4])
+    assert np.array_equal(got["nsteps"][nb], ref["nsteps"][nb])
+    assert handle.last_total_steps() == int(got["nsteps"].sum())
+
+
+def test_render_row_sharding_is_exact(handle):
+    """Multi-GPU partition property: the union of row-cyclic shards IS the frame (bit-for-bit), and the
+    per-shard step totals add up to the whole frame's (checksum of checksums)."""
+    import schw_b200
+    from schw_b200.multigpu import unpermute_rows
+    h, w = 90, 128
+    tex = synthetic_sky(h, w, 4)
+    sc = schw_b200.make_scene(height=h, width=w, delta=0.05)
+    full = handle.render(sc, tex, extras=True)
+    total = handle.last_total_steps()
+    for world in (2, 4, 7):
+        parts, steps = [], 0
+        for r in range(world):
+            parts.append(handle.render(sc, tex, r, h, world, extras=True))
+            steps += handle.last_total_steps()
+        assert steps == total
+        for key in ("rgb", "cls"):
+            assert np.array_equal(unpermute_rows([p[key] for p in parts], h), full[key])
+        fq = unpermute_rows([p["final_q"].reshape(-1, w, 4) for p in parts], h)
+        assert np.array_equal(fq.reshape(-1, 4), full["final_q"], equal_nan=True)
+    # empty shard (more ranks than rows) and error paths
+    empty = handle.render(sc, tex, 5, 5, 1)
+    assert empty["rgb"].shape == (0, w, 3)
+    with pytest.raises(ValueError):
+        handle.render(sc, tex, 0, h + 1, 1)
+    with pytest.raises(ValueError):
+        handle.render(sc, tex[:, :-1], 0, h, 1)
+
+
+def test_render_full_size_properties_1080p(handle):
+    """BASELINE config 3 at full size, through size-independent properties: the up/down and left/right
+    mirror symmetry of the scene (beta -> -beta, pi - beta gives the same planar geodesic), the analytic
+    shadow mask alpha0 <= bh_angle being all 'bh', every escaped ray ending in [r_max, r_max + one step)."""
+    import schw_b200
+    h, w = 1080, 1920
+    tex = synthetic_sky(h, w, 9)
+    sc = schw_b200.make_scene(height=h, width=w)
+    got = handle.render(sc, tex, extras=True)
+    cls = got["cls"]
+    assert np.array_equal(cls, cls[::-1, :]) and np.array_equal(cls, cls[:, ::-1])
+    r = got["final_q"][:, 1].reshape(h, w)
+    esc = cls == 2
+    # mirrored pixels differ by an ulp in (i+0.5)/h, so escaped rays agree to rounding, not bit-for-bit
+    assert relerr(r[::-1, :][esc], r[esc]).max() < 1e-9 and relerr(r[:, ::-1][esc], r[esc]).max() < 1e-9
+    alpha0 = got["ic"][:, 4].reshape(h, w)
+    bh_angle = np.arcsin(3 * np.sqrt(3) * 2.0 / 30.0) / 2
+    assert (cls[alpha0 <= bh_angle] == 0).all() and (cls[alpha0 > bh_angle] == 2).all()
+    assert (r[esc] >= 31.0).all() and (r[esc] < 31.0 + 0.011).all()
+    ns = got["nsteps"].reshape(h, w)
+    assert ns[esc].min() > 4000 and ns[esc].max() < 20000
+    assert handle.last_total_steps() == int(got["nsteps"].astype(np.int64).sum())
+    # every escaped pixel shows a texel of the sky
+    uv = got["uv"].reshape(h, w, 2)
+    assert np.array_equal(got["rgb"][esc], tex[uv[..., 0][esc], uv[..., 1][esc]])
