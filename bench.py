@@ -185,7 +185,12 @@ def main():
     d_cls = torch.empty((max_rows, w), dtype=torch.uint8, device=dev)
     d_all = torch.empty((world, max_rows, 4 * w), dtype=torch.uint8, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # A dedicated (non-default) torch stream: the C ABI treats a NULL stream as "the handle's own stream", and
+    # torch.cuda.Event only sees work on torch's current stream, so kernels and events must share this one.
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step_device():
         hd.render_dev(scene, d_tex.data_ptr(), rb, re, rs, d_rgb.data_ptr(), d_cls.data_ptr(), stream=stream)
