@@ -155,6 +155,11 @@ int  schw_flat_render(schw_handle *h, const schw_scene *scene, const uint8_t *te
  * (FMA = 2 flops), the denominator of the FP64 roofline (not in MEASURED_PEAKS.json). */
 int  schw_fp64_peak_probe(schw_handle *h, double *tflops, float *ms);
 
+/* Diagnostic: evaluates the kernels' own reciprocal and sincos primitives (csrc/schw_device.cuh:
+ * fast_rcp, sincos_flow — the replacements for the reference's `/` and np.sin/np.cos inside
+ * simulation/cuda_geodesic.py:433-474) on n host values, for accuracy tests. */
+int  schw_math_probe(schw_handle *h, const double *x, int64_t n, double *rcp, double *sn, double *cs);
+
 #ifdef __cplusplus
 }
 #endif

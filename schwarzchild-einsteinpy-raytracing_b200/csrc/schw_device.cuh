@@ -8,7 +8,9 @@
 //   * one sincos per flow instead of 3 sin + 1 cos;
 //   * the trailing A(d/2) of step k and the leading A(d/2) of step k+1 read the same (q1,p2)
 //     (A only writes p1,q2), so they are evaluated once and applied as A(d);
-//   * the mixed flow uses pre-halved cos/sin(2 w d) computed once on the host.
+//   * the mixed flow is applied as a small correction q -= w, p -= z with (1-cos(2 w d))/2 and
+//     sin(2 w d)/2 computed once on the host (10 instead of 24 flops per component);
+//   * a branch-free sincos with constant-bank coefficients (no slow path, no UMOV traffic).
 // These change rounding at the ulp level only (the reference's own GPU build already differs
 // from its CPU simulator by FMA contraction); parity is asserted at 1e-9 relative on final
 // states and bit-exact on class / texel (tests/).
@@ -27,7 +29,7 @@ struct StepParams {
     double rs;       // 2*mass                             (cuda_geodesic.py:635)
     double rcap;     // 1.1*rs evaluated in FP64           (cuda_geodesic.py:598)
     double r_max;
-    double hmc, hms; // 0.5*cos(2 w d), 0.5*sin(2 w d)     (cuda_geodesic.py:545-546)
+    double mg, mhs;  // (1-cos(2 w d))/2, sin(2 w d)/2   (cuda_geodesic.py:545-546; cos/sin from host libm)
     int32_t steps;
     int32_t _pad;
 };
@@ -63,10 +65,11 @@ struct RayState {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Reciprocal for the flow: MUFU.RCP64H seed + Newton (cubic then quadratic).  D = r (r-rs) sin th
-// is a normal, non-zero number on every ray the reference handles (it divides by the same
-// factors), so no special-case path is needed: inf/NaN/0 propagate as NaN and the ray ends as
-// 'in_domain' exactly like a NaN in the reference.
+// Reciprocal for the flow: MUFU.RCP64H seed (~2^-20) + one cubic Newton step (error e^3 ~ 2^-60,
+// i.e. below half an ulp before the final rounding).  D = r (r-rs) sin th is a normal, non-zero
+// number on every ray the reference handles (it divides by the same factors), so no special-case
+// path is needed: inf/NaN/0 propagate as NaN and the ray ends as 'in_domain' exactly like a NaN in
+// the reference.  Accuracy is checked on the device in tests/test_gpu_math.py.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double fast_rcp(double x)
 {
@@ -74,9 +77,63 @@ __device__ __forceinline__ double fast_rcp(double x)
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
     e = fma(e, e, e);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
     return fma(y, e, y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sincos for the flow.  Branch-free, no slow path: Cody-Waite reduction by pi/2 with FMA (valid to
+// 1 ulp of the reduced argument for |x| < 2^20; theta of a geodesic stays O(1)), fdlibm minimax
+// kernels on [-pi/4, pi/4] (|err| < 2^-58), quadrant fix-up with integer selects.  Coefficients live
+// in the constant bank so every DFMA takes them as a c[][] operand (no UMOV traffic on the issue
+// port, which this kernel shares almost 1:1 with the FP64 pipe).  19 FP64 instructions.
+// ---------------------------------------------------------------------------------------------
+__constant__ double kTrig[18] = {
+    0.63661977236758138,        //  0  2/pi
+    6755399441055744.0,         //  1  1.5 * 2^52 (round-to-nearest-integer magic)
+    1.5707963267948966,         //  2  pi/2 hi
+    6.123233995736766e-17,      //  3  pi/2 lo
+    -1.66666666666666324348e-01,  //  4  S1
+    8.33333333332248946124e-03,   //  5  S2
+    -1.98412698298579493134e-04,  //  6  S3
+    2.75573137070700676789e-06,   //  7  S4
+    -2.50507602534068634195e-08,  //  8  S5
+    1.58969099521155010221e-10,   //  9  S6
+    4.16666666666666019037e-02,   // 10  C1
+    -1.38888888888741095749e-03,  // 11  C2
+    2.48015872894767294178e-05,   // 12  C3
+    -2.75573143513906633035e-07,  // 13  C4
+    2.08757232129817482790e-09,   // 14  C5
+    -1.13596475577881948265e-11,  // 15  C6
+    0.0, 0.0};
+
+__device__ __forceinline__ void sincos_flow(double x, double &s, double &c)
+{
+    const double t = fma(x, kTrig[0], kTrig[1]);
+    const int q = __double2loint(t);
+    const double fq = t - kTrig[1];
+    double r = fma(-fq, kTrig[2], x);
+    r = fma(-fq, kTrig[3], r);
+    const double z = r * r;
+    double ps = fma(z, kTrig[9], kTrig[8]);
+    double pc = fma(z, kTrig[15], kTrig[14]);
+    ps = fma(z, ps, kTrig[7]);
+    pc = fma(z, pc, kTrig[13]);
+    ps = fma(z, ps, kTrig[6]);
+    pc = fma(z, pc, kTrig[12]);
+    ps = fma(z, ps, kTrig[5]);
+    pc = fma(z, pc, kTrig[11]);
+    ps = fma(z, ps, kTrig[4]);
+    pc = fma(z, pc, kTrig[10]);
+    const double sv = fma(z * r, ps, r);                 // sin(r)
+    const double cv = fma(z, fma(z, pc, -0.5), 1.0);     // cos(r)
+    // quadrant: sin(x) = {sv, cv, -sv, -cv}[q&3], cos(x) = {cv, -sv, -cv, sv}[q&3]
+    const bool odd = q & 1;
+    int shi = __double2hiint(odd ? cv : sv), slo = __double2loint(odd ? cv : sv);
+    int chi = __double2hiint(odd ? sv : cv), clo = __double2loint(odd ? sv : cv);
+    shi ^= (q & 2) << 30;
+    chi ^= ((q + 1) & 2) << 30;
+    s = __hiloint2double(shi, slo);
+    c = __hiloint2double(chi, clo);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -97,7 +154,7 @@ __device__ __forceinline__ void flow(double r, double th,
                                      double hh, double rs)
 {
     double s, c;
-    sincos(th, &s, &c);
+    sincos_flow(th, s, c);
     const double d   = r - rs;
     const double ds  = d * s;
     const double rsn = r * s;
@@ -126,17 +183,17 @@ __device__ __forceinline__ void flow(double r, double th,
     Qp = fma(hh, w * A4, Qp);
 }
 
-// _flow_mixed_dev, cuda_geodesic.py:528-566, for one component.
-__device__ __forceinline__ void mix(double &q1, double &p1, double &q2, double &p2, double hmc, double hms)
+// _flow_mixed_dev, cuda_geodesic.py:528-566, for one component.  With g = (1-cos)/2, hs = sin/2:
+//   q1' = (q1+q2)/2 + (q1-q2) cos/2 + (p1-p2) sin/2 = q1 - w,   q2' = q2 + w,   w = qd g - pd hs
+//   p1' = p1 - z,  p2' = p2 + z,  z = pd g + qd hs
+// (1 - cos(2wd) is exact in FP64 by Sterbenz, so g carries exactly the reference's rounded cosine.)
+__device__ __forceinline__ void mix(double &q1, double &p1, double &q2, double &p2, double g, double hs)
 {
-    const double qs = q1 + q2, qd = q1 - q2;
-    const double ps = p1 + p2, pd = p1 - p2;
-    const double u = fma(pd, hms, qd * hmc);
-    const double v = fma(-qd, hms, pd * hmc);
-    q1 = fma(0.5, qs, u);
-    q2 = fma(0.5, qs, -u);
-    p1 = fma(0.5, ps, v);
-    p2 = fma(0.5, ps, -v);
+    const double qd = q1 - q2, pd = p1 - p2;
+    const double w = fma(qd, g, -(pd * hs));
+    const double z = fma(pd, g, qd * hs);
+    q1 -= w; q2 += w;
+    p1 -= z; p2 += z;
 }
 
 __device__ __forceinline__ void flow_A(RayState &S, double hh, double rs)
@@ -147,12 +204,12 @@ __device__ __forceinline__ void flow_B(RayState &S, double hh, double rs)
 {
     flow(S.q2r, S.q2h, S.p1t, S.p1r, S.p1h, S.p1p, S.p2r, S.p2h, S.q1t, S.q1r, S.q1h, S.q1p, hh, rs);
 }
-__device__ __forceinline__ void flow_C(RayState &S, double hmc, double hms)
+__device__ __forceinline__ void flow_C(RayState &S, double g, double hs)
 {
-    mix(S.q1t, S.p1t, S.q2t, S.p2t, hmc, hms);
-    mix(S.q1r, S.p1r, S.q2r, S.p2r, hmc, hms);
-    mix(S.q1h, S.p1h, S.q2h, S.p2h, hmc, hms);
-    mix(S.q1p, S.p1p, S.q2p, S.p2p, hmc, hms);
+    mix(S.q1t, S.p1t, S.q2t, S.p2t, g, hs);
+    mix(S.q1r, S.p1r, S.q2r, S.p2r, g, hs);
+    mix(S.q1h, S.p1h, S.q2h, S.p2h, g, hs);
+    mix(S.q1p, S.p1p, S.q2p, S.p2p, g, hs);
 }
 
 // B(d/2) C(d) B(d/2): the part of _fantasy_step_ord2 (cuda_geodesic.py:569-575) between the two
@@ -160,7 +217,7 @@ __device__ __forceinline__ void flow_C(RayState &S, double hmc, double hms)
 __device__ __forceinline__ void step_BCB(RayState &S, const StepParams &P)
 {
     flow_B(S, P.h, P.rs);
-    flow_C(S, P.hmc, P.hms);
+    flow_C(S, P.mg, P.mhs);
     flow_B(S, P.h, P.rs);
 }
 

@@ -26,7 +26,13 @@
 
 namespace schw {
 
-constexpr int kBlock = 128;          // threads per CTA
+#ifndef SCHW_BLOCK
+#define SCHW_BLOCK 128
+#endif
+#ifndef SCHW_MINBLOCKS
+#define SCHW_MINBLOCKS 4
+#endif
+constexpr int kBlock = SCHW_BLOCK;   // threads per CTA (tuning variants: make VARIANT_FLAGS=-DSCHW_BLOCK=.. OUT=..)
 constexpr unsigned kFull = 0xffffffffu;
 
 struct Counters {
@@ -127,7 +133,7 @@ __device__ __forceinline__ void park(RayState &S, const StepParams &P)
 }
 
 template <class Job>
-__global__ void __launch_bounds__(kBlock, 4)
+__global__ void __launch_bounds__(kBlock, SCHW_MINBLOCKS)
 persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepParams P, Counters *ctr)
 {
     __shared__ double2 s_slot[kBlock];
@@ -352,6 +358,16 @@ __global__ void flat_kernel(const __grid_constant__ FlatParams fp, const uint8_t
     rgb[3 * k] = r8; rgb[3 * k + 1] = g8; rgb[3 * k + 2] = b8;
 }
 
+// Device math primitives of the flow, exposed for accuracy tests (tests/test_gpu_math.py).
+__global__ void math_probe_kernel(const double *__restrict__ x, long long n, double *__restrict__ rcp,
+                                  double *__restrict__ sn, double *__restrict__ cs)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    rcp[k] = fast_rcp(x[k]);
+    sincos_flow(x[k], sn[k], cs[k]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // FP64 peak probe: 8 independent DFMA chains per thread, register resident.
 // ---------------------------------------------------------------------------------------------
@@ -524,8 +540,8 @@ static int make_step_params(int64_t steps, double delta, double rs, double r_max
     P.rcap = 1.1 * rs;
     P.r_max = r_max;
     const double ang = 2.0 * omega * delta;
-    P.hmc = 0.5 * cos(ang);
-    P.hms = 0.5 * sin(ang);
+    P.mg = 0.5 * (1.0 - cos(ang));      // 1 - cos is exact (Sterbenz): g carries the reference's rounded cosine
+    P.mhs = 0.5 * sin(ang);
     P.steps = (int32_t)steps;
     P._pad = 0;
     return SCHW_OK;
@@ -924,6 +940,26 @@ extern "C" int schw_flat_render(schw_handle *h, const schw_scene *s, const uint8
     CU(cudaGetLastError());
     end_timed(h, st);
     CU(cudaMemcpyAsync(rgb, h->rgb.p, n * 3, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SCHW_OK;
+}
+
+// ---- device math probe (diagnostic) -------------------------------------------------------------
+extern "C" int schw_math_probe(schw_handle *h, const double *x, int64_t n, double *rcp, double *sn, double *cs)
+{
+    if (!h || n < 0 || (n > 0 && (!x || !rcp || !sn || !cs))) return fail(SCHW_E_INVALID, "bad argument");
+    CU(cudaSetDevice(h->device));
+    if (n == 0) return SCHW_OK;
+    cudaStream_t st = h->stream;
+    const size_t b = (size_t)n * 8;
+    ENSURE(h->in_a, b); ENSURE(h->in_b, b); ENSURE(h->in_c, b); ENSURE(h->fq, b);
+    CU(cudaMemcpyAsync(h->in_a.p, x, b, cudaMemcpyHostToDevice, st));
+    math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const double *)h->in_a.p, (long long)n, (double *)h->in_b.p,
+                                                                    (double *)h->in_c.p, (double *)h->fq.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(rcp, h->in_b.p, b, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sn, h->in_c.p, b, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cs, h->fq.p, b, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return SCHW_OK;
 }

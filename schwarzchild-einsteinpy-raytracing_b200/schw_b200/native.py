@@ -10,7 +10,8 @@ import subprocess
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "lib", "libschw_b200.so")
+# SCHW_B200_LIB selects a tuning variant of the same library (tools/build_variants.sh); default is the in-tree build
+LIB_PATH = os.environ.get("SCHW_B200_LIB") or os.path.join(_PKG, "lib", "libschw_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 
 CLASSES = ("bh", "numerical error", "escape_bg", "escape_no_patch", "in_domain")
@@ -22,7 +23,7 @@ EXPORTS = (
     "schw_abi_version", "schw_last_error", "schw_create", "schw_destroy", "schw_device_info",
     "schw_last_kernel_ms", "schw_integrate_batch", "schw_integrate_batch_dev", "schw_integrate_batch_full",
     "schw_initial_conditions", "schw_initial_conditions_px", "schw_classify", "schw_render", "schw_render_dev", "schw_last_total_steps",
-    "schw_flat_render", "schw_fp64_peak_probe",
+    "schw_flat_render", "schw_fp64_peak_probe", "schw_math_probe",
 )
 
 
@@ -90,6 +91,7 @@ def load():
     L.schw_render.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop]
     L.schw_render_dev.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop, vp]
     L.schw_flat_render.argtypes = [vp, scp, vp, vp]
+    L.schw_math_probe.argtypes = [vp, dp, i64, dp, dp, dp]
     L.schw_fp64_peak_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     for name in EXPORTS:
         if name not in ("schw_last_error",):
@@ -171,6 +173,12 @@ class Handle:
         t, ms = C.c_double(), C.c_float()
         _check(self._L.schw_fp64_peak_probe(self._h, C.byref(t), C.byref(ms)))
         return t.value, ms.value
+
+    def math_probe(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        r, s, c = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
+        _check(self._L.schw_math_probe(self._h, _p(x), x.size, _p(r), _p(s), _p(c)))
+        return r, s, c
 
     # -- integrator -----------------------------------------------------------------------------
     def integrate_batch(self, q0s, p0s, steps, delta, rs, r_max, omega, want_steps=False):
