@@ -147,14 +147,36 @@ __device__ __forceinline__ void sincos_flow(double x, double &s, double &c)
 //   dH/dth = -cos(th) ir^2 is^3 pph^2
 //   g.p    = ( -r id pt, (1-rs ir) pr, ir^2 pth, ir^2 is^2 pph )
 // ---------------------------------------------------------------------------------------------
+// sin/cos of the polar angle of one phase-space copy, remembered together with the angle they were
+// computed for.  The trig of a flow is re-evaluated only when the angle's BITS changed since the
+// last evaluation in some lane of the warp (warp-uniform decision, so no divergence).  This is an
+// exact memoisation, not an approximation: results are bit-identical with it on or off.  It pays
+// because every camera ray of the reference starts in the equatorial plane with p_theta = -0.0
+// (utils.py:129,172) and its theta never leaves the double nearest pi/2 (the per-flow increments
+// are ~1e-19, far below half an ulp), while rays with genuine polar motion just pay one compare +
+// vote per flow.
+struct TrigMemo {
+    double th, s, c;
+};
+
+template <bool kMemo>
 __device__ __forceinline__ void flow(double r, double th,
                                      double pt, double pr, double ph, double pp,
                                      double &Pr, double &Ph,                       // momenta updated
                                      double &Qt, double &Qr, double &Qh, double &Qp,  // positions updated
-                                     double hh, double rs)
+                                     double hh, double rs, TrigMemo &m)
 {
     double s, c;
-    sincos_flow(th, s, c);
+    if (kMemo) {
+        const bool same = __double_as_longlong(th) == __double_as_longlong(m.th);
+        if (!__all_sync(0xffffffffu, same)) {
+            sincos_flow(th, m.s, m.c);
+            m.th = th;
+        }
+        s = m.s; c = m.c;
+    } else {
+        sincos_flow(th, s, c);
+    }
     const double d   = r - rs;
     const double ds  = d * s;
     const double rsn = r * s;
@@ -196,13 +218,27 @@ __device__ __forceinline__ void mix(double &q1, double &p1, double &q2, double &
     p1 -= z; p2 += z;
 }
 
-__device__ __forceinline__ void flow_A(RayState &S, double hh, double rs)
+struct Memo2 {
+    TrigMemo m1, m2;      // for theta of copy 1 (flow A) and copy 2 (flow B)
+    // start from a consistent entry (theta = the double nearest pi/2, where parked lanes and every
+    // camera ray live); the memo is keyed by the angle's bits, so it can never go stale
+    __device__ __forceinline__ void invalidate()
+    {
+        m1.th = 1.5707963267948966;
+        sincos_flow(m1.th, m1.s, m1.c);
+        m2 = m1;
+    }
+};
+
+template <bool kMemo>
+__device__ __forceinline__ void flow_A(RayState &S, double hh, double rs, Memo2 &M)
 {
-    flow(S.q1r, S.q1h, S.p2t, S.p2r, S.p2h, S.p2p, S.p1r, S.p1h, S.q2t, S.q2r, S.q2h, S.q2p, hh, rs);
+    flow<kMemo>(S.q1r, S.q1h, S.p2t, S.p2r, S.p2h, S.p2p, S.p1r, S.p1h, S.q2t, S.q2r, S.q2h, S.q2p, hh, rs, M.m1);
 }
-__device__ __forceinline__ void flow_B(RayState &S, double hh, double rs)
+template <bool kMemo>
+__device__ __forceinline__ void flow_B(RayState &S, double hh, double rs, Memo2 &M)
 {
-    flow(S.q2r, S.q2h, S.p1t, S.p1r, S.p1h, S.p1p, S.p2r, S.p2h, S.q1t, S.q1r, S.q1h, S.q1p, hh, rs);
+    flow<kMemo>(S.q2r, S.q2h, S.p1t, S.p1r, S.p1h, S.p1p, S.p2r, S.p2h, S.q1t, S.q1r, S.q1h, S.q1p, hh, rs, M.m2);
 }
 __device__ __forceinline__ void flow_C(RayState &S, double g, double hs)
 {
@@ -214,11 +250,12 @@ __device__ __forceinline__ void flow_C(RayState &S, double g, double hs)
 
 // B(d/2) C(d) B(d/2): the part of _fantasy_step_ord2 (cuda_geodesic.py:569-575) between the two
 // A half-flows.  After it q1 is final for this step (the trailing A does not touch q1).
-__device__ __forceinline__ void step_BCB(RayState &S, const StepParams &P)
+template <bool kMemo>
+__device__ __forceinline__ void step_BCB(RayState &S, const StepParams &P, Memo2 &M)
 {
-    flow_B(S, P.h, P.rs);
+    flow_B<kMemo>(S, P.h, P.rs, M);
     flow_C(S, P.mg, P.mhs);
-    flow_B(S, P.h, P.rs);
+    flow_B<kMemo>(S, P.h, P.rs, M);
 }
 
 // Termination test of cuda_geodesic.py:598 / :623 on copy 1, plus NaN (a NaN r never terminates
@@ -226,6 +263,11 @@ __device__ __forceinline__ void step_BCB(RayState &S, const StepParams &P)
 __device__ __forceinline__ bool terminated(double r, const StepParams &P)
 {
     return (r <= P.rcap) || (r >= P.r_max);
+}
+// "not strictly inside (rcap, r_max)": the same test with NaN counted as finished (two compares).
+__device__ __forceinline__ bool finished_or_nan(double r, const StepParams &P)
+{
+    return !((r > P.rcap) && (r < P.r_max));
 }
 
 __device__ __forceinline__ void init_state(RayState &S, const double q0[4], const double p0[4])

@@ -132,7 +132,7 @@ __device__ __forceinline__ void park(RayState &S, const StepParams &P)
     init_state(S, q0, p0);
 }
 
-template <class Job>
+template <class Job, bool kMemo>
 __global__ void __launch_bounds__(kBlock, SCHW_MINBLOCKS)
 persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepParams P, Counters *ctr)
 {
@@ -140,6 +140,8 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     double2 &slot = s_slot[threadIdx.x];
     const unsigned lane = threadIdx.x & 31u;
     RayState S;
+    Memo2 M;
+    M.invalidate();
     long long k = -1;            // current ray, -1 = none
     int n = 0;                   // steps taken by the current ray
     unsigned long long my_steps = 0;
@@ -183,13 +185,13 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
         while (true) {
             const double hA = fresh ? P.h : P.delta;
             fresh = false;
-            flow_A(S, hA, P.rs);
-            step_BCB(S, P);
+            flow_A<kMemo>(S, hA, P.rs, M);
+            step_BCB<kMemo>(S, P, M);
             ++n;
-            const bool nan_r = !(S.q1r == S.q1r);
-            const bool done = (k >= 0) && (n >= P.steps || terminated(S.q1r, P) || nan_r);
+            const bool done = (k >= 0) && (n >= P.steps || finished_or_nan(S.q1r, P));
             if (__any_sync(kFull, done)) {
                 if (done) {
+                    const bool nan_r = !(S.q1r == S.q1r);
                     job.store(k, S, n, nan_r, slot);
                     my_steps += (unsigned long long)n;
                     k = -1; want = true;
@@ -224,6 +226,7 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
         const double p0[4] = {p0s[4 * i], p0s[4 * i + 1], p0s[4 * i + 2], p0s[4 * i + 3]};
         init_state(S, q0, p0);
     }
+    Memo2 M;      // unused (kMemo = false): the trajectory kernel is store-bound
     double2 *row = reinterpret_cast<double2 *>(out_traj + (size_t)i * (size_t)P.steps * 4);
     long long rows = 0;
     bool fresh = true;
@@ -242,9 +245,9 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
             rows = P.steps;
             break;
         }
-        flow_A(S, fresh ? P.h : P.delta, P.rs);
+        flow_A<false>(S, fresh ? P.h : P.delta, P.rs, M);
         fresh = false;
-        step_BCB(S, P);
+        step_BCB<false>(S, P, M);
     }
     if (out_rows) out_rows[i] = rows;
     atomicAdd(&ctr->total_steps, (unsigned long long)(rows > 0 ? rows - 1 : 0));
@@ -475,8 +478,8 @@ extern "C" int schw_create(int device, schw_handle **out)
     CU(cudaEventCreate(&h->ev1));
     CU(cudaMalloc(&h->ctr, sizeof(Counters)));
     CU(cudaMemset(h->ctr, 0, sizeof(Counters)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_render, persistent_rays<RenderJob>, kBlock, 0));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_batch, persistent_rays<BatchJob>, kBlock, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_render, persistent_rays<RenderJob, true>, kBlock, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_batch, persistent_rays<BatchJob, true>, kBlock, 0));
     if (h->occ_render < 1 || h->occ_batch < 1) return fail(SCHW_E_CUDA, "kernel does not fit on an SM");
     *out = h;
     return SCHW_OK;
@@ -612,6 +615,17 @@ static void end_timed(schw_handle *h, cudaStream_t st)
     h->timed = true;
 }
 
+// SCHW_TRIG_MEMO=0 disables the exact sin/cos memoisation (A/B measurements; results are bit-identical).
+static bool trig_memo_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SCHW_TRIG_MEMO");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 template <class Job>
 static int launch_persistent(schw_handle *h, const Job &job, const StepParams &P, int occ, cudaStream_t st)
 {
@@ -620,7 +634,10 @@ static int launch_persistent(schw_handle *h, const Job &job, const StepParams &P
     long long want_blocks = (job.n + kBlock - 1) / kBlock;
     long long grid = (long long)h->sm_count * occ;
     if (grid > want_blocks) grid = want_blocks;
-    persistent_rays<Job><<<(unsigned)grid, kBlock, 0, st>>>(job, P, h->ctr);
+    if (trig_memo_enabled())
+        persistent_rays<Job, true><<<(unsigned)grid, kBlock, 0, st>>>(job, P, h->ctr);
+    else
+        persistent_rays<Job, false><<<(unsigned)grid, kBlock, 0, st>>>(job, P, h->ctr);
     h->launches += 1;
     CU(cudaGetLastError());
     return SCHW_OK;
