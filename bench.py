@@ -183,7 +183,7 @@ def main():
     d_out = torch.zeros((max_rows, 4 * w), dtype=torch.uint8, device=dev)
     d_rgb = torch.empty((max_rows, w, 3), dtype=torch.uint8, device=dev)
     d_cls = torch.empty((max_rows, w), dtype=torch.uint8, device=dev)
-    d_all = torch.empty((world, max_rows, 4 * w), dtype=torch.uint8, device=dev) if world > 1 else None
+    d_all = torch.empty((world * max_rows, 4 * w), dtype=torch.uint8, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     # A dedicated (non-default) torch stream: the C ABI treats a NULL stream as "the handle's own stream", and
     # torch.cuda.Event only sees work on torch's current stream, so kernels and events must share this one.

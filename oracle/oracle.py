@@ -55,6 +55,7 @@ def lib():
         L.orc_classify.argtypes = [C.POINTER(OrcScene), dp, dp, dp, C.c_int64, bp, bp, bp, dp, i32p]
         L.orc_render.argtypes = [C.POINTER(OrcScene), bp, C.c_int, C.c_int, C.c_int, bp, bp, dp, dp, dp, i32p, ip,
                                  C.c_int]
+        L.orc_flat_render.argtypes = [C.POINTER(OrcScene), bp, bp]
         _lib = L
     return _lib
 
@@ -168,3 +169,11 @@ def render(scene, tex, row_begin=0, row_end=None, row_stride=1, nthreads=0, extr
                           _ptr(rgb, C.c_uint8), _ptr(cls, C.c_uint8), _dp(fq), _dp(ic), _dp(hit),
                           _ptr(uv, C.c_int32), _ptr(ns, C.c_int64), int(nthreads))
     return dict(rgb=rgb, cls=cls, final_q=fq, ic=ic, hit=hit, uv=uv, nsteps=ns, rc=rc)
+
+
+def flat_render(scene, tex):
+    """background.py:99-132 (patch centre already resolved by the caller, :54-58)."""
+    tex = np.ascontiguousarray(tex, np.uint8)
+    rgb = np.zeros((scene.height, scene.width, 3), np.uint8)
+    lib().orc_flat_render(C.byref(scene), _ptr(tex, C.c_uint8), _ptr(rgb, C.c_uint8))
+    return rgb

@@ -445,6 +445,82 @@ int orc_render(const orc_scene *sc, const uint8_t *tex, int row_begin, int row_e
     return rc;
 }
 
+/* ------------------------------------------------------------------------ */
+/*  Flat-space comparison render: save_no_gravity_image_with_background,     */
+/*  simulation/background.py:30-66 (set-up) and :99-132 (CPU pixel loop)     */
+/* ------------------------------------------------------------------------ */
+static void cross3(const double a[3], const double b[3], double o[3])
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static int in_phi_patch(double phi, double phi0, double phi1)     /* background.py:8-17 */
+{
+    phi = pymod(phi, ORC_TWO_PI); phi0 = pymod(phi0, ORC_TWO_PI); phi1 = pymod(phi1, ORC_TWO_PI);
+    if (phi0 <= phi1) return phi0 <= phi && phi <= phi1;
+    return phi >= phi0 || phi <= phi1;
+}
+
+/* Uses sc->obs, fov, height, width, r_max (boundary_radius), patch_*, flip_*.  The caller passes the patch
+ * centre already resolved (antipode of the observer unless override_patch_center, background.py:54-58). */
+int orc_flat_render(const orc_scene *sc, const uint8_t *tex, uint8_t *rgb)
+{
+    int h = sc->height, w = sc->width;
+    const double *obs = sc->obs;
+    double nrm = sqrt(obs[0] * obs[0] + obs[1] * obs[1] + obs[2] * obs[2]);
+    double axis[3] = { (0.0 - obs[0]) / nrm, (0.0 - obs[1]) / nrm, (0.0 - obs[2]) / nrm };
+    double up_guess[3] = { 0, 0, 1 }, cr[3], right[3], up[3];
+    cross3(axis, up_guess, cr);
+    if (fabs(cr[0]) <= 1e-8 && fabs(cr[1]) <= 1e-8 && fabs(cr[2]) <= 1e-8) { up_guess[1] = 1; up_guess[2] = 0; }
+    cross3(up_guess, axis, right);
+    double rn = sqrt(right[0] * right[0] + right[1] * right[1] + right[2] * right[2]);
+    for (int a = 0; a < 3; ++a) right[a] /= rn;
+    cross3(axis, right, up);
+    double un = sqrt(up[0] * up[0] + up[1] * up[1] + up[2] * up[2]);
+    for (int a = 0; a < 3; ++a) up[a] /= un;
+    double plane_dist = 0.2 * nrm, pc[3];
+    for (int a = 0; a < 3; ++a) pc[a] = obs[a] + axis[a] * plane_dist;
+    double plane_width = 2 * plane_dist * tan(sc->fov / 2);
+    double plane_height = plane_width * ((double)h / (double)w);
+    double theta0 = sc->patch_center_theta - sc->patch_size_theta / 2;
+    double theta1 = sc->patch_center_theta + sc->patch_size_theta / 2;
+    double phi0 = sc->patch_center_phi - sc->patch_size_phi / 2;
+    double phi1 = sc->patch_center_phi + sc->patch_size_phi / 2;
+    double phi_span = pymod(phi1 - phi0, ORC_TWO_PI);
+    if (phi_span == 0) phi_span = ORC_TWO_PI;
+    double cc = (obs[0] * obs[0] + obs[1] * obs[1] + obs[2] * obs[2]) - sc->r_max * sc->r_max;
+    for (int i = 0; i < h; ++i)
+        for (int j = 0; j < w; ++j) {
+            uint8_t *o = rgb + ((size_t)i * w + j) * 3;
+            o[0] = o[1] = o[2] = 0;
+            double u = (j + 0.5) / w - 0.5, v = (i + 0.5) / h - 0.5, d[3];
+            for (int a = 0; a < 3; ++a) d[a] = ((pc[a] + (u * plane_width) * right[a]) + (v * plane_height) * up[a]) - obs[a];
+            double dn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            for (int a = 0; a < 3; ++a) d[a] /= dn;
+            double qa = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            double qb = 2 * (obs[0] * d[0] + obs[1] * d[1] + obs[2] * d[2]);
+            double disc = qb * qb - 4 * qa * cc;
+            if (disc < 0) continue;
+            double t = (-qb + sqrt(disc)) / (2 * qa);
+            double hp[3] = { obs[0] + t * d[0], obs[1] + t * d[1], obs[2] + t * d[2] };
+            double r = sqrt(hp[0] * hp[0] + hp[1] * hp[1] + hp[2] * hp[2]);
+            double theta = acos(hp[2] / r), phi = atan2(hp[1], hp[0]);
+            if (theta >= theta0 && theta <= theta1 && in_phi_patch(phi, phi0, phi1)) {
+                double theta_map = sc->flip_theta ? (M_PI - theta) : theta;
+                double phi_map = sc->flip_phi ? -phi : phi;
+                int64_t ub = (int64_t)((theta_map - theta0) / (theta1 - theta0) * (h - 1));
+                double phi_mod = pymod(phi_map - phi0, ORC_TWO_PI);
+                int64_t vb = (int64_t)(phi_mod / phi_span * (w - 1));
+                if (ub < 0) ub = 0; if (ub > h - 1) ub = h - 1;
+                if (vb < 0) vb = 0; if (vb > w - 1) vb = w - 1;
+                const uint8_t *tx = tex + ((size_t)ub * w + vb) * 3;
+                o[0] = tx[0]; o[1] = tx[1]; o[2] = tx[2];
+            }
+        }
+    return 0;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

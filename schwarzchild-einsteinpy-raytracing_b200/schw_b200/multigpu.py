@@ -55,9 +55,9 @@ def gather_row_blocks(local, height, world, rank, device=None):
     if t.shape[0] < max_rows:
         pad = torch.zeros((max_rows - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         t = torch.cat([t, pad], 0)
-    full = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(full, t.contiguous())
-    full = full.cpu().numpy()
+    full = torch.empty((world * max_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(full, t.contiguous())          # rank blocks concatenated along dim 0
+    full = full.view((world, max_rows) + tuple(t.shape[1:])).cpu().numpy()
     return unpermute_rows([full[r] for r in range(world)], height)
 
 

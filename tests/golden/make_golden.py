@@ -20,7 +20,7 @@ into .npz as well.
 
 Usage:  python tests/golden/make_golden.py <part> [<part> ...]
 Parts:  kat single ic stepper_default stepper_general render_R1 render_R2
-        render_R3 render_R4 render_R5   (or "all")
+        render_R3 render_R4 render_R5 flat_F1 flat_F2 flat_F3   (or "all")
 """
 import base64
 import json
@@ -304,14 +304,45 @@ def part_render(name):
         note="reference run_manual_simulation (raytracing.py:16-314), random.seed(0), n_samples=2, texture_card.png")
 
 
+FLATS = {
+    "F1": dict(h=40, w=56, obs_x=30, fov=80.0, r_max=31, pct=90, pcp=180, pst=180, psp=360, flt=False, flp=False, override=False),
+    "F2": dict(h=36, w=48, obs_x=20.0, fov=90.0, r_max=21.0, pct=100, pcp=205, pst=70, psp=110, flt=True, flp=True, override=True),
+    "F3": dict(h=32, w=32, obs_x=30, fov=80.0, r_max=31, pct=90, pcp=300, pst=126, psp=224, flt=False, flp=True, override=True),
+}
+
+
+def part_flat(name):
+    """Reference flat-space render (simulation/background.py:19-141, CPU loop) on the texture card."""
+    from simulation.blackhole import Observer
+    from simulation.background import save_no_gravity_image_with_background
+    from PIL import Image
+    c = FLATS[name]
+    tex_path = f"{OUT}/texture_card.png"
+    tmp = tempfile.mkdtemp(prefix=f"golden_{name}_")
+    obs = Observer(position=np.array([c["obs_x"], 0, 0]), fov=np.radians(c["fov"]), image_size=(c["h"], c["w"]))
+    save_no_gravity_image_with_background(
+        obs, tex_path, f"{tmp}/images/no_gravity.png", boundary_radius=c["r_max"],
+        patch_center_theta=np.deg2rad(c["pct"]), patch_center_phi=np.deg2rad(c["pcp"]),
+        patch_size_theta=np.deg2rad(c["pst"]), patch_size_phi=np.deg2rad(c["psp"]),
+        flip_theta=c["flt"], flip_phi=c["flp"], return_sampled_trajectories=False, override_patch_center=c["override"])
+    img = np.array(Image.open(f"{tmp}/images/no_gravity.png").convert("RGB"))
+    bg = np.array(Image.open(tex_path).convert("RGB").resize((c["w"], c["h"]), Image.LANCZOS))
+    np.savez_compressed(f"{OUT}/flat_{name}.npz", img=img, bg_array=bg, cfg=json.dumps(c),
+                        note="reference save_no_gravity_image_with_background (background.py:19-141), texture_card.png")
+    print("flat", name, img.shape, "nonblack", int(np.any(img != 0, axis=2).sum()))
+
+
 def main():
     install_stubs()
     parts = sys.argv[1:] or ["all"]
     if parts == ["all"]:
-        parts = ["kat", "single", "ic", "stepper_default", "stepper_general"] + [f"render_{k}" for k in RENDERS]
+        parts = (["kat", "single", "ic", "stepper_default", "stepper_general"] + [f"render_{k}" for k in RENDERS]
+                 + [f"flat_{k}" for k in FLATS])
     for p in parts:
         if p.startswith("render_"):
             part_render(p.split("_", 1)[1])
+        elif p.startswith("flat_"):
+            part_flat(p.split("_", 1)[1])
         else:
             globals()[f"part_{p}"]()
 

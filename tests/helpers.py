@@ -85,3 +85,17 @@ def random_rays(n, seed, equatorial_frac=0.5):
         q0s[k] = [0.0, r0, th0, ph0]
         p0s[k] = [pt if k % 2 else -pt, pr, pth, pph]
     return q0s, p0s
+
+
+def flat_scene_kwargs(cfg):
+    """Scene kwargs of a flat golden (tests/golden/make_golden.py FLATS), patch centre resolved like background.py:54-58."""
+    c = json.loads(str(cfg))
+    if c["override"]:
+        pct, pcp = np.deg2rad(c["pct"]), np.deg2rad(c["pcp"])
+    else:
+        opp = -np.array([c["obs_x"], 0, 0])
+        pct, pcp = np.arccos(opp[2] / np.linalg.norm(opp)), np.arctan2(opp[1], opp[0])
+    return dict(obs=(float(c["obs_x"]), 0.0, 0.0), fov=np.radians(c["fov"]), height=c["h"], width=c["w"],
+                r_max=float(c["r_max"]), patch_center_theta=float(pct), patch_center_phi=float(pcp),
+                patch_size_theta=np.deg2rad(c["pst"]), patch_size_phi=np.deg2rad(c["psp"]),
+                flip_theta=c["flt"], flip_phi=c["flp"])

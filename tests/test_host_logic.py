@@ -1,0 +1,96 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU calls)."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+
+REFERENCE_DEFAULTS = dict(                      # config.py:6-32 of the reference (types matter: 31 and 30 are ints)
+    size=200, fov=80.0, background='images/backgrounds/milky-way-equirec.jpg', steps=200000, delta=0.01, omega=0.01,
+    rtol=1e-2, atol=1e-2, order=2, suppress_warnings=False, cuda=True, bh_mass=1.0, boundary_radius=31,
+    observer_distance=30, bg_patch_center_theta=90, bg_patch_center_phi=180, bg_patch_center_theta_relobs=0,
+    bg_patch_center_phi_relobs=0, bg_patch_size_theta=180, bg_patch_size_phi=360, bg_flip_theta=False,
+    bg_flip_phi=False, no_flat_trajectories=False)
+
+
+def test_config_flags_and_defaults_match_reference():
+    import config
+    a = vars(config.parse_args([]))
+    for k, v in REFERENCE_DEFAULTS.items():
+        assert a[k] == v and type(a[k]) is type(v), k
+    b = config.parse_args(["--size", "400", "--bg-flip-phi", "--boundary-radius", "21", "--order", "4"])
+    assert b.size == 400 and b.bg_flip_phi and b.boundary_radius == 21.0 and b.order == 4
+    with pytest.raises(SystemExit):
+        config.parse_args(["--order", "3"])
+    # additive flags default to the reference's behaviour (square frame)
+    assert a["width"] is None and a["height"] is None
+
+
+def test_scene_classes():
+    from simulation.blackhole import BlackHole, Observer
+    bh = BlackHole(mass=1.5)
+    assert bh.rs == 3.0 and bh.position.shape == (3,)
+    ob = Observer(position=[30, 0, 0], fov=1.0, image_size=(4, 6))
+    assert ob.image_size == (4, 6) and ob.position.dtype.kind == "i"
+
+
+def test_null_momentum_helpers_vs_reference_golden(golden):
+    """angles_to_p_sph + build_null_4momentum_ep_sph reproduce the reference's p0 from its own alpha0."""
+    from simulation.utils import angles_to_p_sph, build_null_4momentum_ep_sph
+    g = golden("ic_golden.npz")["table"]
+    for row in g[::37]:
+        obs_x, mass = row[0], row[4]
+        p0_ref, alpha0 = row[11:15], row[15]
+        p_sp = angles_to_p_sph(alpha0, 0.0, obs_x, mass_bh=mass)
+        p0 = build_null_4momentum_ep_sph(p_sp, np.array([obs_x, np.pi / 2, 0.0]), mass_bh=mass, future=True)
+        # alpha0 = acos(cos alpha) loses ~1e-16/sin(alpha) near the image centre, times r_obs in p_phi
+        assert relerr(p0, p0_ref, 1.0).max() < 1e-11
+        assert np.signbit(p0[2])
+        pm = build_null_4momentum_ep_sph(p_sp, np.array([obs_x, np.pi / 2, 0.0]), mass_bh=mass, future=False)
+        assert pm[0] == -p0[0]
+    with pytest.raises(ValueError):
+        build_null_4momentum_ep_sph([1, 0, 0], [1.9, np.pi / 2, 0.0])
+
+
+def test_apply_relative_offsets():
+    from simulation.utils import _apply_relative_offsets
+    th, ph = _apply_relative_offsets(90, 180, 0, 0)
+    assert th == np.pi / 2 and ph == np.pi
+    th, ph = _apply_relative_offsets(90, 180, 100, 200)          # clip to [0, pi], wrap to [0, 2 pi)
+    assert th == np.pi and abs(ph - np.deg2rad(20)) < 1e-15
+    th, ph = _apply_relative_offsets(10, 10, -30, -25)
+    assert th == 0.0 and abs(ph - np.deg2rad(345)) < 1e-15
+
+
+def test_row_sharding_helpers():
+    from schw_b200.multigpu import rows_of, shard_rows, unpermute_rows
+    for h in (1, 7, 16, 2160):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                rb, re, rs = shard_rows(h, r, world)
+                rows = list(range(rb, re, rs))
+                assert len(rows) == rows_of(h, r, world)
+                seen += rows
+            assert sorted(seen) == list(range(h))
+            full = np.arange(h * 3).reshape(h, 3)
+            max_rows = (h + world - 1) // world
+            blocks = []
+            for r in range(world):
+                b = np.zeros((max_rows, 3), full.dtype)
+                b[:rows_of(h, r, world)] = full[r::world]
+                blocks.append(b)
+            assert np.array_equal(unpermute_rows(blocks, h), full)
+
+
+def test_run_manual_simulation_quirks_without_gpu(tmp_path, monkeypatch):
+    """Reference quirks reproduced on the host side: n_samples=0 returns an all-black frame (App. D-3);
+    the CPU branch does not exist (App. D-2)."""
+    from simulation.blackhole import BlackHole, Observer
+    from simulation.raytracing import run_manual_simulation
+    monkeypatch.chdir(tmp_path)
+    bh = BlackHole(1.0); ob = Observer(np.array([30, 0, 0]), np.radians(80), (6, 8))
+    img = run_manual_simulation(bh, ob, steps=10, delta=0.1, use_cuda=True, boundary_radius=31, n_samples=0)
+    assert img.shape == (6, 8, 3) and img.dtype == np.uint8 and not img.any()
+    with pytest.raises(RuntimeError):
+        run_manual_simulation(bh, ob, steps=10, delta=0.1, use_cuda=False, boundary_radius=31, n_samples=2)

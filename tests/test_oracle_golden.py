@@ -152,3 +152,15 @@ def test_k3_conditioning(orc, golden):
     assert d[:2500].max() < 1e-12
     assert 1e-11 < d[4000:5000].max() < 1e-7
     assert 1e-9 < d[6000:6600].max() < 1e-5
+
+
+def test_flat_render_vs_reference(orc, golden):
+    """N1: save_no_gravity_image_with_background (background.py:19-141).  F1 is the main.py default, which the
+    reference renders all black (phi0 % 2pi == phi1 % 2pi == 0 for a 360-degree patch, background.py:8-17)."""
+    from helpers import flat_scene_kwargs
+    for name in ("F1", "F2", "F3"):
+        g = golden(f"flat_{name}.npz")
+        img = orc.flat_render(orc.make_scene(**flat_scene_kwargs(g["cfg"])), g["bg_array"])
+        mism = np.any(img != g["img"], axis=2).mean()
+        assert mism <= 2e-3, (name, mism)          # truncating texel map: a pixel may flip on an integer boundary
+    assert not golden("flat_F1.npz")["img"].any()
