@@ -3,8 +3,8 @@
 // Everything here is FP64, one ray per thread, state in registers.  The formulas are the
 // reference's (file:line cited per function, relative to the reference checkout) but the
 // evaluation is re-derived for the B200 FP64 pipe (64 DFMA lanes / SM):
-//   * one reciprocal per Hamiltonian flow instead of nine divisions: with D = r (r-rs) sin(th),
-//     1/r, 1/(r-rs) and 1/sin(th) are R*(r-rs)*sin, R*r*sin and R*r*(r-rs);
+//   * two reciprocals per Hamiltonian flow instead of nine divisions: R = 1/(r (r-rs)) gives
+//     1/r = R (r-rs) and 1/(r-rs) = R r; 1/sin(th) belongs to the memoised trig factors;
 //   * one sincos per flow instead of 3 sin + 1 cos;
 //   * the trailing A(d/2) of step k and the leading A(d/2) of step k+1 read the same (q1,p2)
 //     (A only writes p1,q2), so they are evaluated once and applied as A(d);
@@ -26,6 +26,7 @@ namespace schw {
 struct StepParams {
     double h;        // 0.5*delta                         (cuda_geodesic.py:571-575)
     double delta;    // full step, used for merged A(d)
+    double h_rs, d_rs; // h*rs, delta*rs
     double rs;       // 2*mass                             (cuda_geodesic.py:635)
     double rcap;     // 1.1*rs evaluated in FP64           (cuda_geodesic.py:598)
     double r_max;
@@ -66,8 +67,8 @@ struct RayState {
 
 // ---------------------------------------------------------------------------------------------
 // Reciprocal for the flow: MUFU.RCP64H seed (~2^-20) + one cubic Newton step (error e^3 ~ 2^-60,
-// i.e. below half an ulp before the final rounding).  D = r (r-rs) sin th is a normal, non-zero
-// number on every ray the reference handles (it divides by the same factors), so no special-case
+// i.e. below half an ulp before the final rounding).  r (r-rs) and sin th are normal, non-zero
+// numbers on every ray the reference handles (it divides by the same factors), so no special-case
 // path is needed: inf/NaN/0 propagate as NaN and the ray ends as 'in_domain' exactly like a NaN in
 // the reference.  Accuracy is checked on the device in tests/test_gpu_math.py.
 // ---------------------------------------------------------------------------------------------
@@ -147,8 +148,8 @@ __device__ __forceinline__ void sincos_flow(double x, double &s, double &c)
 //   dH/dth = -cos(th) ir^2 is^3 pph^2
 //   g.p    = ( -r id pt, (1-rs ir) pr, ir^2 pth, ir^2 is^2 pph )
 // ---------------------------------------------------------------------------------------------
-// sin/cos of the polar angle of one phase-space copy, remembered together with the angle they were
-// computed for.  The trig of a flow is re-evaluated only when the angle's BITS changed since the
+// The trig factors of the polar angle of one phase-space copy (1/sin, cos/sin), remembered together
+// with the angle they were computed for.  The trig of a flow is re-evaluated only when the angle's BITS changed since the
 // last evaluation in some lane of the warp (warp-uniform decision, so no divergence).  This is an
 // exact memoisation, not an approximation: results are bit-identical with it on or off.  It pays
 // because every camera ray of the reference starts in the equatorial plane with p_theta = -0.0
@@ -156,51 +157,57 @@ __device__ __forceinline__ void sincos_flow(double x, double &s, double &c)
 // are ~1e-19, far below half an ulp), while rays with genuine polar motion just pay one compare +
 // vote per flow.
 struct TrigMemo {
-    double th, s, c;
+    double th;     // the angle the entry was computed for (compared bitwise)
+    double is;     // 1 / sin(th)
+    double cis;    // cos(th) / sin(th)
 };
+
+// The two trig-derived factors a flow needs: 1/sin(th) and cos(th)/sin(th).
+__device__ __forceinline__ void trig_factors(double th, double &is, double &cis)
+{
+    double s, c;
+    sincos_flow(th, s, c);
+    is = fast_rcp(s);
+    cis = c * is;
+}
 
 template <bool kMemo>
 __device__ __forceinline__ void flow(double r, double th,
                                      double pt, double pr, double ph, double pp,
                                      double &Pr, double &Ph,                       // momenta updated
                                      double &Qt, double &Qr, double &Qh, double &Qp,  // positions updated
-                                     double hh, double rs, TrigMemo &m)
+                                     double hh, double hrs, double rs, TrigMemo &m)   // hrs = hh*rs
 {
-    double s, c;
+    double is, cis;
     if (kMemo) {
         const bool same = __double_as_longlong(th) == __double_as_longlong(m.th);
         if (!__all_sync(0xffffffffu, same)) {
-            sincos_flow(th, m.s, m.c);
+            trig_factors(th, m.is, m.cis);
             m.th = th;
         }
-        s = m.s; c = m.c;
+        is = m.is; cis = m.cis;
     } else {
-        sincos_flow(th, s, c);
+        trig_factors(th, is, cis);
     }
     const double d   = r - rs;
-    const double ds  = d * s;
-    const double rsn = r * s;
-    const double rd  = r * d;
-    const double R   = fast_rcp(rd * s);
-    const double ir  = R * ds;
-    const double id  = R * rsn;
-    const double is  = R * rd;
-    const double f   = fma(-rs, ir, 1.0);
+    const double R   = fast_rcp(r * d);          // 1 / (r (r - rs))
+    const double ir  = R * d;                    // 1 / r
+    const double id  = R * r;                    // 1 / (r - rs)
     const double A1  = id * pt;
     const double A2  = ir * pr;
     const double A3  = ir * ph;
-    const double w   = ir * is;
+    const double w   = ir * is;                  // 1 / (r sin th)
     const double A4  = w * pp;
     const double k   = A4 * A4;
     const double e   = fma(A3, A3, k);
     double dHr = A1 * A1;
     dHr = fma(A2, A2, dHr);
     dHr = fma(-ir, e, dHr);
-    const double dHh = -(c * is) * k;
+    const double dHh = -cis * k;                 // -cos/sin^3 * pph^2 / r^2
     Pr = fma(-hh, dHr, Pr);
     Ph = fma(-hh, dHh, Ph);
     Qt = fma(-hh, r * A1, Qt);
-    Qr = fma(hh, f * pr, Qr);
+    Qr = fma(-hrs, A2, fma(hh, pr, Qr));         // + hh (1 - rs/r) pr
     Qh = fma(hh, ir * A3, Qh);
     Qp = fma(hh, w * A4, Qp);
 }
@@ -225,20 +232,20 @@ struct Memo2 {
     __device__ __forceinline__ void invalidate()
     {
         m1.th = 1.5707963267948966;
-        sincos_flow(m1.th, m1.s, m1.c);
+        trig_factors(m1.th, m1.is, m1.cis);
         m2 = m1;
     }
 };
 
 template <bool kMemo>
-__device__ __forceinline__ void flow_A(RayState &S, double hh, double rs, Memo2 &M)
+__device__ __forceinline__ void flow_A(RayState &S, double hh, double hrs, double rs, Memo2 &M)
 {
-    flow<kMemo>(S.q1r, S.q1h, S.p2t, S.p2r, S.p2h, S.p2p, S.p1r, S.p1h, S.q2t, S.q2r, S.q2h, S.q2p, hh, rs, M.m1);
+    flow<kMemo>(S.q1r, S.q1h, S.p2t, S.p2r, S.p2h, S.p2p, S.p1r, S.p1h, S.q2t, S.q2r, S.q2h, S.q2p, hh, hrs, rs, M.m1);
 }
 template <bool kMemo>
-__device__ __forceinline__ void flow_B(RayState &S, double hh, double rs, Memo2 &M)
+__device__ __forceinline__ void flow_B(RayState &S, double hh, double hrs, double rs, Memo2 &M)
 {
-    flow<kMemo>(S.q2r, S.q2h, S.p1t, S.p1r, S.p1h, S.p1p, S.p2r, S.p2h, S.q1t, S.q1r, S.q1h, S.q1p, hh, rs, M.m2);
+    flow<kMemo>(S.q2r, S.q2h, S.p1t, S.p1r, S.p1h, S.p1p, S.p2r, S.p2h, S.q1t, S.q1r, S.q1h, S.q1p, hh, hrs, rs, M.m2);
 }
 __device__ __forceinline__ void flow_C(RayState &S, double g, double hs)
 {
@@ -253,9 +260,9 @@ __device__ __forceinline__ void flow_C(RayState &S, double g, double hs)
 template <bool kMemo>
 __device__ __forceinline__ void step_BCB(RayState &S, const StepParams &P, Memo2 &M)
 {
-    flow_B<kMemo>(S, P.h, P.rs, M);
+    flow_B<kMemo>(S, P.h, P.h_rs, P.rs, M);
     flow_C(S, P.mg, P.mhs);
-    flow_B<kMemo>(S, P.h, P.rs, M);
+    flow_B<kMemo>(S, P.h, P.h_rs, P.rs, M);
 }
 
 // Termination test of cuda_geodesic.py:598 / :623 on copy 1, plus NaN (a NaN r never terminates

@@ -184,8 +184,9 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
         // ---- integrate until some lane of the warp finishes its ray ----
         while (true) {
             const double hA = fresh ? P.h : P.delta;
+            const double hArs = fresh ? P.h_rs : P.d_rs;
             fresh = false;
-            flow_A<kMemo>(S, hA, P.rs, M);
+            flow_A<kMemo>(S, hA, hArs, P.rs, M);
             step_BCB<kMemo>(S, P, M);
             ++n;
             const bool done = (k >= 0) && (n >= P.steps || finished_or_nan(S.q1r, P));
@@ -245,7 +246,7 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
             rows = P.steps;
             break;
         }
-        flow_A<false>(S, fresh ? P.h : P.delta, P.rs, M);
+        flow_A<false>(S, fresh ? P.h : P.delta, fresh ? P.h_rs : P.d_rs, P.rs, M);
         fresh = false;
         step_BCB<false>(S, P, M);
     }
@@ -545,6 +546,8 @@ static int make_step_params(int64_t steps, double delta, double rs, double r_max
     if (steps < 0 || steps > 0x7fffffffLL) return fail(SCHW_E_INVALID, "steps must be in [0, 2^31-1]");
     P.h = 0.5 * delta;
     P.delta = delta;
+    P.h_rs = P.h * rs;
+    P.d_rs = delta * rs;
     P.rs = rs;
     P.rcap = 1.1 * rs;
     P.r_max = r_max;
