@@ -157,9 +157,9 @@ __device__ __forceinline__ void sincos_flow(double x, double &s, double &c)
 // are ~1e-19, far below half an ulp), while rays with genuine polar motion just pay one compare +
 // vote per flow.
 struct TrigMemo {
-    double th;        // the angle the entry was computed for (compared bitwise); register
-    double2 *fac;     // this thread's shared-memory slot: (1/sin(th), cos(th)/sin(th)) -- kept out of
-                      // the register file so that 8 CTAs x 128 threads fit on an SM (64 registers/thread)
+    double th;     // the angle the entry was computed for (compared bitwise)
+    double is;     // 1 / sin(th)
+    double cis;    // cos(th) / sin(th)
 };
 
 // The two trig-derived factors a flow needs: 1/sin(th) and cos(th)/sin(th).
@@ -182,12 +182,10 @@ __device__ __forceinline__ void flow(double r, double th,
     if (kMemo) {
         const bool same = __double_as_longlong(th) == __double_as_longlong(m.th);
         if (!__all_sync(0xffffffffu, same)) {
-            trig_factors(th, is, cis);
-            *m.fac = make_double2(is, cis);
+            trig_factors(th, m.is, m.cis);
             m.th = th;
         }
-        const double2 v = *m.fac;
-        is = v.x; cis = v.y;
+        is = m.is; cis = m.cis;
     } else {
         trig_factors(th, is, cis);
     }
@@ -231,13 +229,11 @@ struct Memo2 {
     TrigMemo m1, m2;      // for theta of copy 1 (flow A) and copy 2 (flow B)
     // start from a consistent entry (theta = the double nearest pi/2, where parked lanes and every
     // camera ray live); the memo is keyed by the angle's bits, so it can never go stale
-    __device__ __forceinline__ void init(double2 *slot1, double2 *slot2)
+    __device__ __forceinline__ void invalidate()
     {
-        double is, cis;
-        m1.th = m2.th = 1.5707963267948966;
-        trig_factors(m1.th, is, cis);
-        m1.fac = slot1; m2.fac = slot2;
-        if (slot1) { *slot1 = make_double2(is, cis); *slot2 = make_double2(is, cis); }
+        m1.th = 1.5707963267948966;
+        trig_factors(m1.th, m1.is, m1.cis);
+        m2 = m1;
     }
 };
 

@@ -139,10 +139,9 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     __shared__ double2 s_slot[kBlock];
     double2 &slot = s_slot[threadIdx.x];
     const unsigned lane = threadIdx.x & 31u;
-    __shared__ double2 s_memo[kMemo ? 2 * kBlock : 2];
     RayState S;
     Memo2 M;
-    M.init(kMemo ? &s_memo[threadIdx.x] : nullptr, kMemo ? &s_memo[kBlock + threadIdx.x] : nullptr);
+    M.invalidate();
     long long k = -1;            // current ray, -1 = none
     int n = 0;                   // steps taken by the current ray
     unsigned long long my_steps = 0;
@@ -229,7 +228,6 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
         init_state(S, q0, p0);
     }
     Memo2 M;      // unused (kMemo = false): the trajectory kernel is store-bound
-    M.init(nullptr, nullptr);
     double2 *row = reinterpret_cast<double2 *>(out_traj + (size_t)i * (size_t)P.steps * 4);
     long long rows = 0;
     bool fresh = true;
