@@ -18,6 +18,7 @@ ap.add_argument("--height", type=int, default=540)
 ap.add_argument("--width", type=int, default=960)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--delta", type=float, default=0.01)
+ap.add_argument("--stride", type=int, default=1, help="render rows 0::stride only (one rank's shard of a stride-way split)")
 ap.add_argument("--batch", type=int, default=0, help="also time integrate_batch on N random non-equatorial rays")
 a = ap.parse_args()
 
@@ -26,10 +27,10 @@ rng = np.random.default_rng(0)
 tex = rng.integers(0, 256, size=(a.height, a.width, 3), dtype=np.uint8)
 sc = schw_b200.make_scene(height=a.height, width=a.width, delta=a.delta)
 for r in range(a.reps):
-    out = hd.render(sc, tex)
+    out = hd.render(sc, tex, 0, a.height, a.stride)
     ms, n = hd.last_kernel_ms()
     steps = hd.last_total_steps()
-    print(f"render {a.width}x{a.height}: kernel {ms:.3f} ms, {steps} steps, {steps / ms * 1e-6:.3f} Gsteps/s, "
+    print(f"render {a.width}x{a.height} rows 0::{a.stride}: kernel {ms:.3f} ms, {steps} steps, {steps / ms * 1e-6:.3f} Gsteps/s, "
           f"{312 * steps / ms * 1e-9:.2f} algorithmic TFLOP/s")
 if a.batch:
     n = a.batch
