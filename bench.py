@@ -161,7 +161,7 @@ def main():
     import torch
     import torch.distributed as dist
     import schw_b200
-    from schw_b200.multigpu import gather_row_blocks, shard_rows, rows_of
+    from schw_b200.multigpu import render_frame, shard_rows, rows_of
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -233,11 +233,8 @@ def main():
 
     # ---- e2e: the host-buffer C-ABI call a user makes (texture H2D + outputs D2H inside the timed region) ----
     def step_e2e():
-        out = hd.render(scene, tex_host.numpy(), rb, re, rs)
-        if world > 1:
-            packed = np.concatenate([out["rgb"].reshape(nloc, 3 * w), out["cls"]], axis=1)
-            return gather_row_blocks(packed, h, world, rank, dev)
-        return out["rgb"]
+        # the call a user of the package makes: host texture in, host frame out (sharded + gathered when world > 1)
+        return render_frame(scene, tex_host.numpy(), handle=hd)["rgb"]
     step_e2e()
     barrier()
     t0 = time.perf_counter()

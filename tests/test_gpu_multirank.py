@@ -1,0 +1,69 @@
+"""Two real ranks (one process per GPU, NCCL): `render_frame` — row-cyclic shards, one device-side
+all_gather, un-permutation — must reproduce the single-GPU frame bit for bit, diagnostics included.
+Skipped on a one-GPU box (NCCL cannot put two ranks on one device); CPU coverage of the same host
+logic is tests/test_multigpu_gloo.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import PKG, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, h, w, q):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    import schw_b200
+    from schw_b200.multigpu import render_frame
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        rng = np.random.default_rng(5)
+        tex = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        sc = schw_b200.make_scene(height=h, width=w, delta=0.05)
+        hd = schw_b200.Handle(rank)
+        got = render_frame(sc, tex, extras=True, handle=hd)
+        ok = True
+        if rank == 0:
+            ref = hd.render(sc, tex, extras=True)
+            ok = (np.array_equal(got["rgb"], ref["rgb"]) and np.array_equal(got["cls"], ref["cls"])
+                  and np.array_equal(got["final_q"], ref["final_q"], equal_nan=True)
+                  and np.array_equal(got["ic"], ref["ic"]) and np.array_equal(got["uv"], ref["uv"])
+                  and np.array_equal(got["nsteps"], ref["nsteps"]) and got["rgb"].any())
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_render_frame_two_ranks_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (one rank per GPU)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world, h, w = 2, 77, 130          # odd row count: the ranks get 39 and 38 rows
+    procs = [ctx.Process(target=_worker, args=(r, world, port, h, w, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5) for _ in range(world)) == [(0, True), (1, True)]
