@@ -96,32 +96,55 @@ def render_frame(scene, tex, extras=False, handle=None):
     import torch.distributed as dist
     dev = torch.device("cuda", torch.cuda.current_device())
     max_rows = (h + world - 1) // world
-    nloc = rows_of(h, rank, world)
-    d_tex = torch.from_numpy(np.ascontiguousarray(tex, np.uint8)).to(dev) if tex is not None else None
-    d_rgb = torch.zeros((max_rows, w, 3), dtype=torch.uint8, device=dev)
-    d_cls = torch.zeros((max_rows, w), dtype=torch.uint8, device=dev)
-    ex = {}
-    if extras:
-        ex = dict(final_q=torch.zeros((max_rows, w, 4), dtype=torch.float64, device=dev),
-                  ic=torch.zeros((max_rows, w, 9), dtype=torch.float64, device=dev),
-                  hit=torch.zeros((max_rows, w, 2), dtype=torch.float64, device=dev),
-                  uv=torch.zeros((max_rows, w, 2), dtype=torch.int32, device=dev),
-                  nsteps=torch.zeros((max_rows, w), dtype=torch.int32, device=dev))
-    hd.render_dev(scene, d_tex.data_ptr() if d_tex is not None else 0, rb, re, rs, d_rgb.data_ptr(), d_cls.data_ptr(),
-                  stream=_torch_stream_ptr(),
+    B = _buffers(dev, h, w, world, extras, tex is not None)
+    if tex is not None:
+        B["tex"].copy_(torch.from_numpy(np.ascontiguousarray(tex, np.uint8)), non_blocking=True)
+    ex = B["extras"]
+    hd.render_dev(scene, B["tex"].data_ptr() if tex is not None else 0, rb, re, rs,
+                  B["rgb"].data_ptr(), B["cls"].data_ptr(), stream=_torch_stream_ptr(),
                   d_final_q=ex["final_q"].data_ptr() if extras else 0, d_ic=ex["ic"].data_ptr() if extras else 0,
                   d_hit=ex["hit"].data_ptr() if extras else 0, d_texel=ex["uv"].data_ptr() if extras else 0,
                   d_nsteps=ex["nsteps"].data_ptr() if extras else 0)
-    packed = torch.cat([d_rgb.view(max_rows, 3 * w), d_cls], dim=1)                   # (max_rows, 4w) u8
-    full = torch.empty((world * max_rows, 4 * w), dtype=torch.uint8, device=dev)
-    dist.all_gather_into_tensor(full, packed)                                          # THE collective of a frame
-    full = full.view(world, max_rows, 4 * w).cpu().numpy()
-    img = unpermute_rows([full[r] for r in range(world)], h)
+    torch.cat([B["rgb"].view(max_rows, 3 * w), B["cls"]], dim=1, out=B["packed"])     # (max_rows, 4w) u8
+    dist.all_gather_into_tensor(B["gathered"], B["packed"])                            # THE collective of a frame
+    # rank blocks -> natural row order on the device: row i = r + world*k lives at [r, k]
+    nat = B["gathered"].view(world, max_rows, 4 * w).permute(1, 0, 2).reshape(world * max_rows, 4 * w)[:h]
+    B["host"].copy_(nat, non_blocking=False)                                           # one D2H into pinned memory
+    img = B["host"].numpy()
     res = dict(rgb=img[:, :3 * w].reshape(h, w, 3).copy(), cls=img[:, 3 * w:].copy(), q0=q0[0])
     for k, t in ex.items():                                                            # diagnostics, on request only
         g = torch.empty((world * max_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
         dist.all_gather_into_tensor(g, t)
-        g = g.view((world, max_rows) + tuple(t.shape[1:])).cpu().numpy()
-        a = unpermute_rows([g[r] for r in range(world)], h)
+        g = g.view((world, max_rows) + tuple(t.shape[1:])).transpose(0, 1).reshape((world * max_rows,) + tuple(t.shape[1:]))[:h]
+        a = g.cpu().numpy()
         res[k] = a.reshape(h * w, -1) if a.ndim == 3 else a.reshape(h * w)
     return res
+
+
+_BUF = {}
+
+
+def _buffers(dev, h, w, world, extras, has_tex):
+    """Per-(device, frame shape) device/pinned buffers, reused across frames (sweeps render many frames)."""
+    import torch
+    key = (str(dev), h, w, world)
+    B = _BUF.get(key)
+    max_rows = (h + world - 1) // world
+    if B is None:
+        B = dict(tex=torch.empty((h, w, 3), dtype=torch.uint8, device=dev),
+                 rgb=torch.zeros((max_rows, w, 3), dtype=torch.uint8, device=dev),
+                 cls=torch.zeros((max_rows, w), dtype=torch.uint8, device=dev),
+                 packed=torch.empty((max_rows, 4 * w), dtype=torch.uint8, device=dev),
+                 gathered=torch.empty((world * max_rows, 4 * w), dtype=torch.uint8, device=dev),
+                 host=torch.empty((h, 4 * w), dtype=torch.uint8).pin_memory(), extras={})
+        _BUF.clear()                      # keep one frame shape resident
+        _BUF[key] = B
+    if extras and not B["extras"]:
+        B["extras"] = dict(final_q=torch.zeros((max_rows, w, 4), dtype=torch.float64, device=dev),
+                           ic=torch.zeros((max_rows, w, 9), dtype=torch.float64, device=dev),
+                           hit=torch.zeros((max_rows, w, 2), dtype=torch.float64, device=dev),
+                           uv=torch.zeros((max_rows, w, 2), dtype=torch.int32, device=dev),
+                           nsteps=torch.zeros((max_rows, w), dtype=torch.int32, device=dev))
+    if not extras:
+        return dict(B, extras={})
+    return B
