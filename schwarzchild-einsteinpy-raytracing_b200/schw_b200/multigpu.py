@@ -109,9 +109,10 @@ def render_frame(scene, tex, extras=False, handle=None):
     dist.all_gather_into_tensor(B["gathered"], B["packed"])                            # THE collective of a frame
     # rank blocks -> natural row order on the device: row i = r + world*k lives at [r, k]
     nat = B["gathered"].view(world, max_rows, 4 * w).permute(1, 0, 2).reshape(world * max_rows, 4 * w)[:h]
-    B["host"].copy_(nat, non_blocking=False)                                           # one D2H into pinned memory
-    img = B["host"].numpy()
-    res = dict(rgb=img[:, :3 * w].reshape(h, w, 3).copy(), cls=img[:, 3 * w:].copy(), q0=q0[0])
+    rgb = np.empty((h, w, 3), np.uint8); cls = np.empty((h, w), np.uint8)               # fresh arrays, like the reference's np.zeros
+    torch.from_numpy(rgb).view(h, 3 * w).copy_(nat[:, :3 * w])                         # D2H straight into the results
+    torch.from_numpy(cls).copy_(nat[:, 3 * w:])
+    res = dict(rgb=rgb, cls=cls, q0=q0[0])
     for k, t in ex.items():                                                            # diagnostics, on request only
         g = torch.empty((world * max_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
         dist.all_gather_into_tensor(g, t)
@@ -135,8 +136,7 @@ def _buffers(dev, h, w, world, extras, has_tex):
                  rgb=torch.zeros((max_rows, w, 3), dtype=torch.uint8, device=dev),
                  cls=torch.zeros((max_rows, w), dtype=torch.uint8, device=dev),
                  packed=torch.empty((max_rows, 4 * w), dtype=torch.uint8, device=dev),
-                 gathered=torch.empty((world * max_rows, 4 * w), dtype=torch.uint8, device=dev),
-                 host=torch.empty((h, 4 * w), dtype=torch.uint8).pin_memory(), extras={})
+                 gathered=torch.empty((world * max_rows, 4 * w), dtype=torch.uint8, device=dev), extras={})
         _BUF.clear()                      # keep one frame shape resident
         _BUF[key] = B
     if extras and not B["extras"]:
