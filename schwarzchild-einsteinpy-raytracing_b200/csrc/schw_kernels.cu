@@ -55,20 +55,23 @@ struct BatchJob {
 
     __device__ __forceinline__ long long queue_len() const { return n; }
     __device__ __forceinline__ long long resolve(long long q) const { return q; }
-    __device__ __forceinline__ void load(long long k, RayState &S, double2 &) const
+    // load(): initial (q0, p0) of ray k into this thread's shared-memory staging area st[0..3*kBlock]
+    // (st[0] = (q0_t,q0_r), st[kBlock] = (q0_th,q0_ph), st[2 kBlock] = (p0_t,p0_r), st[3 kBlock] = (p0_th,p0_ph)).
+    __device__ __forceinline__ void load(long long k, double2 *st, double2 &) const
     {
         const double2 *q = reinterpret_cast<const double2 *>(q0s + 4 * k);
         const double2 *p = reinterpret_cast<const double2 *>(p0s + 4 * k);
-        const double2 qa = __ldg(q), qb = __ldg(q + 1), pa = __ldg(p), pb = __ldg(p + 1);
-        const double q0[4] = {qa.x, qa.y, qb.x, qb.y}, p0[4] = {pa.x, pa.y, pb.x, pb.y};
-        init_state(S, q0, p0);
+        st[0] = __ldg(q); st[kBlock] = __ldg(q + 1); st[2 * kBlock] = __ldg(p); st[3 * kBlock] = __ldg(p + 1);
     }
-    __device__ __forceinline__ void store(long long k, const RayState &S, int nsteps, bool nan_exit, const double2 &) const
+    // cost of one divergent service pass (load + store) in lane-steps, for the batching rule of the kernel
+    static constexpr int kServiceCost = 32;
+    __device__ __forceinline__ void store(long long k, double t, double r, double th, double ph, int nsteps, bool nan_exit,
+                                          const double2 &) const
     {
         const double nanv = __longlong_as_double(0x7ff8000000000000LL);
         double2 *o = reinterpret_cast<double2 *>(out_qs + 4 * k);
-        o[0] = nan_exit ? make_double2(nanv, nanv) : make_double2(S.q1t, S.q1r);
-        o[1] = nan_exit ? make_double2(nanv, nanv) : make_double2(S.q1h, S.q1p);
+        o[0] = nan_exit ? make_double2(nanv, nanv) : make_double2(t, r);
+        o[1] = nan_exit ? make_double2(nanv, nanv) : make_double2(th, ph);
         if (out_steps) out_steps[k] = nsteps;
     }
 };
@@ -100,15 +103,15 @@ struct RenderJob {
         const int j = seg * 32 + (int)(q & 31);
         return j < sc.width ? (long long)row * sc.width + j : -1;
     }
-    // slot = this thread's shared-memory (alpha0, beta): kept out of registers across the step loop
-    __device__ __forceinline__ void load(long long k, RayState &S, double2 &slot) const
+    // slot = this thread's shared-memory (alpha0, beta): kept out of registers across the step loop.
+    __device__ __forceinline__ void load(long long k, double2 *st, double2 &slot) const
     {
         const int row = (int)(k / sc.width), j = (int)(k - (long long)row * sc.width);
         const int i = sc.row_begin + row * sc.row_stride;
         RayIC r;
         initial_conditions(sc, i, j, r);
-        const double q0[4] = {0.0, sc.r_obs, sc.th_obs, sc.ph_obs};
-        init_state(S, q0, r.p0);
+        st[0] = make_double2(0.0, sc.r_obs); st[kBlock] = make_double2(sc.th_obs, sc.ph_obs);
+        st[2 * kBlock] = make_double2(r.p0[0], r.p0[1]); st[3 * kBlock] = make_double2(r.p0[2], r.p0[3]);
         slot = make_double2(r.alpha0, r.beta);
         if (ic) {
             double *o = ic + 9 * k;
@@ -117,11 +120,15 @@ struct RenderJob {
             c2s(r.dir[0], r.dir[1], r.dir[2], o[6], o[7], o[8]);
         }
     }
-    __device__ __forceinline__ void store(long long k, const RayState &S, int ns, bool nan_exit, const double2 &slot) const
+    // one service pass = classification epilogue + camera/initial-condition prologue, ~1500 instructions executed for
+    // however few lanes need it = ~9 warp-steps = ~288 lane-steps
+    static constexpr int kServiceCost = 288;
+    __device__ __forceinline__ void store(long long k, double t_, double r_, double th_, double ph_, int ns, bool nan_exit,
+                                          const double2 &slot) const
     {
         const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-        const double t = nan_exit ? nanv : S.q1t, r = nan_exit ? nanv : S.q1r;
-        const double th = nan_exit ? nanv : S.q1h, ph = nan_exit ? nanv : S.q1p;
+        const double t = nan_exit ? nanv : t_, r = nan_exit ? nanv : r_;
+        const double th = nan_exit ? nanv : th_, ph = nan_exit ? nanv : ph_;
         RayHit o;
         classify(sc, tex, r, th, ph, slot.x, slot.y, o);
         uint8_t *c3 = rgb + 3 * k;
@@ -156,78 +163,108 @@ template <class Job, bool kMemo>
 __global__ void __launch_bounds__(kBlock, SCHW_MINBLOCKS)
 persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepParams P, Counters *ctr)
 {
-    __shared__ double2 s_slot[kBlock];
+    __shared__ double2 s_slot[kBlock];        // (alpha0, beta) of the ray in flight, for its epilogue
+    __shared__ double2 s_fin[4 * kBlock];     // staging: final (t,r),(theta,phi) of a finished ray awaiting service;
+                                              // (q0, p0) of a fetched ray between load() and the state registers
+    __shared__ int s_nsteps[kBlock];
+    __shared__ unsigned long long s_total;    // steps integrated by this CTA (metric numerator)
+    if (threadIdx.x == 0) s_total = 0ull;
+    __syncthreads();
     double2 &slot = s_slot[threadIdx.x];
     const unsigned lane = threadIdx.x & 31u;
     RayState S;
     Memo2 M;
     M.invalidate();
-    long long k = -1;            // current ray, -1 = none
-    int n = 0;                   // steps taken by the current ray
-    unsigned long long my_steps = 0;
+    int k = -1;                  // ray in flight, or finished ray awaiting service (n < 2^31 is checked on the host)
+    int n = 0;                   // steps taken by the ray in flight
     bool fresh = false;
-    bool want = true;            // lane needs a ray
+    bool active = false;         // integrating a ray
+    bool waiting = false;        // ray finished: result parked in shared memory, epilogue + refill pending
     bool drained = false;        // queue is empty
+    int it = 0;                  // warp-uniform iteration counter
+    int debt = 0;                // lane-steps spent idle by waiting lanes since the last service (warp-uniform)
 
     // Lanes without a ray sit on a fixed point of all three flows (p = 0 => dq = dH = 0, mixing of
     // equal copies is the identity), so they execute the same instructions without ever producing
-    // inf/NaN operands (which would send sincos down its slow path for the whole warp).
+    // inf/NaN operands (which would send the trig/reciprocal code down slow paths for the whole warp).
     park(S, P);
 
     while (true) {
-        // ---- refill: lanes whose ray ended take the next one (loop: a ray may end at step 0) ----
-        while (true) {
-            const unsigned need = __ballot_sync(kFull, want && !drained);
+        // ---- service (divergent, so batched): epilogue of the finished rays, then refill ----
+        if (waiting) {
+            const double2 a = s_fin[threadIdx.x], b = s_fin[kBlock + threadIdx.x];
+            job.store(k, a.x, a.y, b.x, b.y, s_nsteps[threadIdx.x], !(a.y == a.y), slot);
+            waiting = false; k = -1;
+        }
+        while (true) {                                             // loop: a ray may end at step 0
+            const unsigned need = __ballot_sync(kFull, !active && !drained);
             if (need == 0u) break;
             long long base = 0;
             const int leader = __ffs(need) - 1;
             if ((int)lane == leader) base = (long long)atomicAdd(&ctr->next, (unsigned long long)__popc(need));
             base = __shfl_sync(kFull, base, leader);
-            if (want && !drained) {
+            if (!active && !drained) {
                 const long long mine = base + __popc(need & ((1u << lane) - 1u));
                 if (mine < job.queue_len()) {
-                    k = job.resolve(mine); n = 0;
-                    if (k < 0) continue;                             // empty slot (ragged end of a row): fetch again
-                    job.load(k, S, slot);
-                    if (P.steps <= 0 || terminated(S.q1r, P)) {
-                        job.store(k, S, 0, false, slot);         // cuda_geodesic.py:598: test precedes the first step
-                        k = -1;
-                    } else {
-                        want = false; fresh = true;
+                    const int kk = (int)job.resolve(mine);
+                    if (kk >= 0) {                                 // (< 0: empty slot at the ragged end of a row)
+                        job.load(kk, &s_fin[threadIdx.x], slot);
+                        {
+                            const double2 qa = s_fin[threadIdx.x], qb = s_fin[kBlock + threadIdx.x];
+                            const double2 pa = s_fin[2 * kBlock + threadIdx.x], pb = s_fin[3 * kBlock + threadIdx.x];
+                            const double q0[4] = {qa.x, qa.y, qb.x, qb.y}, p0[4] = {pa.x, pa.y, pb.x, pb.y};
+                            init_state(S, q0, p0);
+                        }
+                        if (P.steps <= 0 || terminated(S.q1r, P)) {
+                            // cuda_geodesic.py:598: the test precedes the first step
+                            job.store(kk, S.q1t, S.q1r, S.q1h, S.q1p, 0, false, slot);
+                            park(S, P);
+                        } else {
+                            k = kk; n = 0; active = true; fresh = true;
+                        }
                     }
                 } else {
-                    drained = true; k = -1;
+                    drained = true;
                 }
             }
         }
-        if (__ballot_sync(kFull, k >= 0) == 0u) break;       // every lane is out of work
+        if (__ballot_sync(kFull, active) == 0u) break;             // every lane is out of work
+        debt = 0;
 
-        // ---- integrate until some lane of the warp finishes its ray ----
+        // ---- integrate; finished lanes park their result and idle until servicing them pays ----
         while (true) {
             const double hA = fresh ? P.h : P.delta;
             const double hArs = fresh ? P.h_rs : P.d_rs;
             fresh = false;
             flow_A<kMemo>(S, hA, hArs, P.rs, M);
             step_BCB<kMemo>(S, P, M);
-            ++n;
-            const bool done = (k >= 0) && (n >= P.steps || finished_or_nan(S.q1r, P));
-            if (__any_sync(kFull, done)) {
+            ++n; ++it;
+            const bool done = active && (n >= P.steps || finished_or_nan(S.q1r, P));
+            const bool any_done = __any_sync(kFull, done);
+            const bool tick = (it & 15) == 0;
+            if (any_done || tick) {
+                // idle cost so far: every waiting lane wastes one lane-step per iteration (booked every 16 iterations)
+                const unsigned wm = __ballot_sync(kFull, waiting);
+                if (tick) debt += __popc(wm) * 16;
                 if (done) {
-                    const bool nan_r = !(S.q1r == S.q1r);
-                    job.store(k, S, n, nan_r, slot);
-                    my_steps += (unsigned long long)n;
-                    k = -1; want = true;
+                    s_fin[threadIdx.x] = make_double2(S.q1t, S.q1r);
+                    s_fin[kBlock + threadIdx.x] = make_double2(S.q1h, S.q1p);
+                    s_nsteps[threadIdx.x] = n;
+                    atomicAdd(&s_total, (unsigned long long)n);
+                    active = false; waiting = true;
                     park(S, P);
-                    n = 0;
                 }
-                break;
+                // Service now if nobody is left integrating, or once the accumulated idle cost reaches the cost of
+                // one (divergent) service pass -- the ski-rental rule: waiting never costs more than 2x the optimum.
+                if ((wm != 0u || any_done) &&
+                    (debt >= Job::kServiceCost || __ballot_sync(kFull, active) == 0u)) break;
             }
         }
     }
 
     // ---- total step count (metric numerator) ----
-    for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_down_sync(kFull, my_steps, o);
-    if (lane == 0 && my_steps) atomicAdd(&ctr->total_steps, my_steps);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_total) atomicAdd(&ctr->total_steps, s_total);
 }
 
 // ---------------------------------------------------------------------------------------------
