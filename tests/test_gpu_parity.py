@@ -312,3 +312,61 @@ def test_render_full_size_properties_1080p(handle):
     # every escaped pixel shows a texel of the sky
     uv = got["uv"].reshape(h, w, 2)
     assert np.array_equal(got["rgb"][esc], tex[uv[..., 0][esc], uv[..., 1][esc]])
+
+
+def test_entry_points_agree_on_a_ragged_frame(handle):
+    """The staged entry points compose to the fused one, bit for bit, on a frame whose width is not a multiple of
+    the 32-pixel work tile and whose rows are visited with a stride (compute-sanitizer is closed on this pool, so
+    this doubles as the out-of-bounds canary: every output array is checked in full)."""
+    import schw_b200
+    rng = np.random.default_rng(0)
+    h, w = 37, 70
+    tex = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    sc = schw_b200.make_scene(height=h, width=w, delta=0.1)
+    a = handle.render(sc, tex, extras=True)
+    b = handle.render(sc, tex, 1, h, 3, extras=True)
+    rows = np.arange(1, h, 3)
+    assert np.array_equal(b["rgb"], a["rgb"][rows]) and np.array_equal(b["cls"], a["cls"][rows])
+    assert np.array_equal(b["final_q"].reshape(len(rows), w, 4), a["final_q"].reshape(h, w, 4)[rows], equal_nan=True)
+    q0s, ic = handle.initial_conditions(sc)
+    assert np.array_equal(ic, a["ic"])
+    out, ns = handle.integrate_batch(q0s, ic[:, :4].copy(), 200000, 0.1, 2.0, 31.0, 1.0, want_steps=True)
+    assert np.array_equal(ns, a["nsteps"]) and np.array_equal(out, a["final_q"], equal_nan=True)
+    c = handle.classify(sc, a["final_q"], ic[:, 4].copy(), ic[:, 5].copy(), tex)
+    assert np.array_equal(c["cls"], a["cls"].reshape(-1)) and np.array_equal(c["rgb"], a["rgb"].reshape(-1, 3))
+    assert np.array_equal(c["uv"], a["uv"]) and np.array_equal(c["hit"], a["hit"], equal_nan=True)
+    traj, nrows = handle.integrate_batch_full(q0s[:7], ic[:7, :4].copy(), 1500, 0.1, 2.0, 31.0, 1.0, want_rows=True)
+    for k in range(7):
+        assert nrows[k] == ns[k] + 1 and np.array_equal(traj[k, nrows[k] - 1], out[k])
+    # repeated launches are deterministic whatever the queue order (SCHW_LPT_ORDER) and lane assignment
+    a2 = handle.render(sc, tex, extras=True)
+    for key in ("rgb", "cls", "final_q", "nsteps", "uv"):
+        assert np.array_equal(a[key], a2[key], equal_nan=True)
+
+
+def test_render_4k_rows_vs_oracle(handle, orc):
+    """BASELINE config 4 at full size: the whole 3840x2160 frame is rendered on the GPU; eight evenly spaced rows
+    (30 720 rays, ~1.8e8 steps) are recomputed by the CPU oracle and compared ray by ray."""
+    import schw_b200
+    h, w = 2160, 3840
+    tex = synthetic_sky(h, w, 7)
+    got = handle.render(schw_b200.make_scene(height=h, width=w), tex)
+    total = handle.last_total_steps()
+    assert 4.85e10 < total < 4.93e10
+    cls = got["cls"]
+    assert np.array_equal(cls, cls[::-1, :]) and np.array_equal(cls, cls[:, ::-1])
+    rows = np.unique(np.floor((np.arange(8) + 0.5) * h / 8).astype(int))
+    sc = orc.make_scene(height=h, width=w)
+    for r in rows:
+        ref = orc.render(sc, tex, int(r), int(r) + 1, 1)
+        sub = handle.render(schw_b200.make_scene(height=h, width=w), tex, int(r), int(r) + 1, 1, extras=True)
+        assert np.array_equal(sub["rgb"][0], got["rgb"][r]) and np.array_equal(sub["cls"][0], got["cls"][r])
+        assert np.array_equal(got["cls"][r], ref["cls"][0])
+        kw = dict(height=h, width=w, patch_center_theta=np.pi / 2, patch_center_phi=np.pi, patch_size_theta=np.pi,
+                  patch_size_phi=2 * np.pi, flip_theta=False)
+        fu, fv = texel_coords(kw, ref["hit"][:, 0], ref["hit"][:, 1])
+        diff = np.any(got["rgb"][r] != ref["rgb"][0], axis=1)
+        assert np.all(near_rounding_boundary(fu, fv)[diff]) and diff.mean() < 5e-3
+        nb = (ref["cls"].reshape(-1) != 0) & ~in_band_g(ref["ic"][:, 0:4])
+        assert np.array_equal(sub["nsteps"][nb], ref["nsteps"][nb])
+        assert state_close(sub["final_q"][nb], ref["final_q"][nb]).all()
