@@ -31,6 +31,16 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+def ncu_summary():
+    """Counters of the dominant kernel from the committed ncu capture of this workload (profiles/ncu_summary.json):
+    DRAM traffic per launch and FP64-pipe utilisation.  They are measured under ncu, so they are quoted with their
+    provenance and never used to compute a bench value."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+    except (OSError, ValueError):
+        return {}
+
+
 ALGO_FLOP_PER_STEP = 312        # SURVEY §8d / App. A-4: 268 add/mul (FMA = 2) + 36 div + 8 sin/cos
 NOMINAL_FP64_TFLOPS = 37.2      # 148 SM x 64 lanes x 2 x 1.965 GHz (BASELINE.md §3)
 
@@ -259,6 +269,7 @@ def main():
         e2e_value = steps_per_frame * args.steps / e2e_s
         # roofline of the dominant kernel (persistent_rays<RenderJob>), per launch, this rank's shard
         achieved = ALGO_FLOP_PER_STEP * steps_per_frame_local / (kern_ms[-1] * 1e-3) / 1e12
+        ncu = ncu_summary() if (h, w) == (2160, 3840) else {}
         line = {
             "metric": "geodesic_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -269,7 +280,11 @@ def main():
                     "d2h_bytes_per_step": int(4 * w * h), "frame_ms": 1e3 * e2e_s / args.steps},
             "gpu_launches": args.steps * world,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops, "traffic": None,
+                         "frac": achieved / peak_tflops,
+                         "traffic": ncu.get("dram_bytes_per_launch") if world == 1 else None,
+                         "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, " + ncu.get("source", "n/a") + ")",
+                         "fp64_pipe_pct_of_peak_ncu": ncu.get("fp64_pipe_pct"),
+                         "algorithmic_bytes_per_launch": 7 * h * w,
                          "peak_source": "measured in this run (schw_fp64_peak_probe: register-resident DFMA chains); "
                                         f"nominal {NOMINAL_FP64_TFLOPS} TFLOP/s",
                          "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,

@@ -106,6 +106,14 @@ int  schw_integrate_batch_full(schw_handle *h, const double *q0s, const double *
                                int64_t steps, double delta, double rs, double r_max, double omega,
                                double *out_traj, int64_t *out_rows);
 
+/* Decimated variant: same integration, but only the rows whose step index is listed in the strictly
+ * ascending row_idx[0..nidx) are produced, out: (n,nidx,4) f64 (zero where the ray ended earlier).  With
+ * row_idx = np.linspace(0, steps-1, min(1000, steps), dtype=int32) this is exactly what the reference keeps of
+ * integrate_batch_full's (n,steps,4) result (simulation/raytracing.py:139-150), without the 6.4 MB/ray buffer. */
+int  schw_integrate_batch_rows(schw_handle *h, const double *q0s, const double *p0s, int64_t n,
+                               int64_t steps, double delta, double rs, double r_max, double omega,
+                               const int32_t *row_idx, int64_t nidx, double *out, int64_t *out_rows);
+
 /* ---- stages 1+2: camera rays -> initial conditions -------------------------------------------
  * Replaces the pixel loop of run_manual_simulation (simulation/raytracing.py:60-88,98-116) and
  * get_initial_conditions / angles_to_p_sph / build_null_4momentum_ep_sph (simulation/utils.py:

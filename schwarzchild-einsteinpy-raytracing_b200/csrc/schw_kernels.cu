@@ -313,6 +313,60 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// Decimated trajectories: the same integration as integrate_full_kernel, but only the rows
+// whose step index appears in the ascending list row_idx[0..nidx) are written, to out (n, nidx, 4).  This is what
+// the reference's consumer keeps anyway (np.linspace over the allocated rows, raytracing.py:139-143), without
+// the (n, steps, 4) buffer (6.4 MB per ray at the default step cap).  Rows the ray never reaches stay zero.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+integrate_rows_kernel(const double *__restrict__ q0s, const double *__restrict__ p0s, long long n,
+                      const __grid_constant__ StepParams P, const int32_t *__restrict__ row_idx, int nidx,
+                      double *__restrict__ out, long long *__restrict__ out_rows, Counters *ctr)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RayState S;
+    {
+        const double q0[4] = {q0s[4 * i], q0s[4 * i + 1], q0s[4 * i + 2], q0s[4 * i + 3]};
+        const double p0[4] = {p0s[4 * i], p0s[4 * i + 1], p0s[4 * i + 2], p0s[4 * i + 3]};
+        init_state(S, q0, p0);
+    }
+    Memo2 M;
+    M.invalidate();
+    double2 *row = reinterpret_cast<double2 *>(out + (size_t)i * (size_t)nidx * 4);
+    int cur = 0;
+    int next = nidx > 0 ? row_idx[0] : -1;
+    long long rows = 0;
+    bool fresh = true;
+    for (int step = 0; step < P.steps; ++step) {
+        const bool nan_r = !(S.q1r == S.q1r);
+        if (step == next) {
+            row[2 * (size_t)cur] = make_double2(S.q1t, S.q1r);
+            row[2 * (size_t)cur + 1] = make_double2(S.q1h, S.q1p);
+            ++cur;
+            next = cur < nidx ? row_idx[cur] : -1;
+        }
+        rows = step + 1;
+        if (terminated(S.q1r, P)) break;
+        if (nan_r) {
+            // NaN never terminates in the reference: every later row is NaN
+            const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+            for (; cur < nidx; ++cur) {
+                row[2 * (size_t)cur] = make_double2(nanv, nanv);
+                row[2 * (size_t)cur + 1] = make_double2(nanv, nanv);
+            }
+            rows = P.steps;
+            break;
+        }
+        flow_A<true>(S, fresh ? P.h : P.delta, fresh ? P.h_rs : P.d_rs, P.rs, M);
+        fresh = false;
+        step_BCB<true>(S, P, M);
+    }
+    if (out_rows) out_rows[i] = rows;
+    atomicAdd(&ctr->total_steps, (unsigned long long)(rows > 0 ? rows - 1 : 0));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stage kernels (boundary / parity testing): one thread per ray, static mapping.
 // ---------------------------------------------------------------------------------------------
 __global__ void ic_kernel(const __grid_constant__ SceneParams sc, long long n, double *__restrict__ q0s,
@@ -799,6 +853,45 @@ extern "C" int schw_integrate_batch_full(schw_handle *h, const double *q0s, cons
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     free(rows);
     if (e != cudaSuccess) return fail(SCHW_E_CUDA, std::string("integrate_batch_full copy-back: ") + cudaGetErrorString(e));
+    return SCHW_OK;
+}
+
+extern "C" int schw_integrate_batch_rows(schw_handle *h, const double *q0s, const double *p0s, int64_t n,
+                                         int64_t steps, double delta, double rs, double r_max, double omega,
+                                         const int32_t *row_idx, int64_t nidx, double *out, int64_t *out_rows)
+{
+    if (!h) return fail(SCHW_E_INVALID, "null handle");
+    if (n < 0 || n > 0x7fffffffLL || nidx < 0 || nidx > 0x7fffffffLL) return fail(SCHW_E_INVALID, "n, nidx must be in [0, 2^31-1]");
+    if (n > 0 && (!q0s || !p0s)) return fail(SCHW_E_INVALID, "null array");
+    if (n > 0 && nidx > 0 && (!row_idx || !out)) return fail(SCHW_E_INVALID, "null array");
+    for (int64_t k = 0; k < nidx; ++k)
+        if (row_idx[k] < 0 || (k > 0 && row_idx[k] <= row_idx[k - 1]))
+            return fail(SCHW_E_INVALID, "row_idx must be strictly ascending and non-negative");
+    CU(cudaSetDevice(h->device));
+    StepParams P;
+    int rc = make_step_params(steps, delta, rs, r_max, omega, P);
+    if (rc) return rc;
+    if (n == 0) return SCHW_OK;
+    const size_t b = (size_t)n * 4 * sizeof(double);
+    const size_t ob = (size_t)n * (size_t)nidx * 4 * sizeof(double);
+    ENSURE(h->in_a, b); ENSURE(h->in_b, b); ENSURE(h->traj, ob + 8); ENSURE(h->rows, (size_t)n * sizeof(long long));
+    ENSURE(h->in_c, (size_t)(nidx + 1) * sizeof(int32_t));
+    cudaStream_t st = h->stream;
+    CU(cudaMemcpyAsync(h->in_a.p, q0s, b, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->in_b.p, p0s, b, cudaMemcpyHostToDevice, st));
+    if (nidx > 0) CU(cudaMemcpyAsync(h->in_c.p, row_idx, (size_t)nidx * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
+    if (ob) CU(cudaMemsetAsync(h->traj.p, 0, ob, st));
+    begin_timed(h, st);
+    integrate_rows_kernel<<<(unsigned)((n + 31) / 32), 32, 0, st>>>((const double *)h->in_a.p, (const double *)h->in_b.p,
+                                                                      (long long)n, P, (const int32_t *)h->in_c.p, (int)nidx,
+                                                                      (double *)h->traj.p, (long long *)h->rows.p, h->ctr);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    end_timed(h, st);
+    if (ob) CU(cudaMemcpyAsync(out, h->traj.p, ob, cudaMemcpyDeviceToHost, st));
+    if (out_rows) CU(cudaMemcpyAsync(out_rows, h->rows.p, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return SCHW_OK;
 }
 

@@ -21,7 +21,7 @@ SCHW_OK, SCHW_E_INVALID, SCHW_E_CUDA, SCHW_E_HORIZON, SCHW_E_NULLCOND, SCHW_E_RA
 # every symbol include/schw_b200.h declares (tests/test_abi_symbols.py checks header <-> library <-> this list)
 EXPORTS = (
     "schw_abi_version", "schw_last_error", "schw_create", "schw_destroy", "schw_device_info",
-    "schw_last_kernel_ms", "schw_integrate_batch", "schw_integrate_batch_dev", "schw_integrate_batch_full",
+    "schw_last_kernel_ms", "schw_integrate_batch", "schw_integrate_batch_dev", "schw_integrate_batch_full", "schw_integrate_batch_rows",
     "schw_initial_conditions", "schw_initial_conditions_px", "schw_classify", "schw_render", "schw_render_dev", "schw_last_total_steps",
     "schw_flat_render", "schw_fp64_peak_probe", "schw_math_probe",
 )
@@ -85,6 +85,7 @@ def load():
     L.schw_integrate_batch.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp]
     L.schw_integrate_batch_dev.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp, vp]
     L.schw_integrate_batch_full.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp]
+    L.schw_integrate_batch_rows.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, vp, i64, dp, vp]
     L.schw_initial_conditions.argtypes = [vp, scp, i32, i32, i32, dp, dp]
     L.schw_initial_conditions_px.argtypes = [vp, dp, dp, i64, dbl, dp, dp]
     L.schw_classify.argtypes = [vp, scp, dp, dp, dp, i64, vp, vp, vp, dp, vp]
@@ -208,6 +209,19 @@ class Handle:
         _check(self._L.schw_integrate_batch_full(self._h, _p(q0s), _p(p0s), n, int(steps), float(delta), float(rs),
                                                  float(r_max), float(omega), _p(traj), _p(rows)))
         return (traj, rows) if want_rows else traj
+
+    def integrate_batch_rows(self, q0s, p0s, steps, delta, rs, r_max, omega, row_idx, want_rows=False):
+        """Rows `row_idx` (strictly ascending step indices) of integrate_batch_full's result, (n, len(row_idx), 4)."""
+        q0s = np.ascontiguousarray(q0s, np.float64); p0s = np.ascontiguousarray(p0s, np.float64)
+        if q0s.ndim != 2 or q0s.shape[1] != 4 or p0s.shape != q0s.shape:
+            raise ValueError("q0s and p0s must both have shape (n, 4)")
+        row_idx = np.ascontiguousarray(row_idx, np.int32)
+        n = q0s.shape[0]
+        out = np.zeros((n, row_idx.size, 4), np.float64)
+        rows = np.zeros(n, np.int64)
+        _check(self._L.schw_integrate_batch_rows(self._h, _p(q0s), _p(p0s), n, int(steps), float(delta), float(rs),
+                                                 float(r_max), float(omega), _p(row_idx), row_idx.size, _p(out), _p(rows)))
+        return (out, rows) if want_rows else out
 
     # -- stages -----------------------------------------------------------------------------------
     def initial_conditions(self, scene, row_begin=0, row_end=None, row_stride=1):

@@ -1,0 +1,43 @@
+"""The bench.py JSON contract, exercised on a small frame (both arms)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+REQUIRED = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+            "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"]
+
+
+def _run(args):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.gpu
+def test_bench_line_small_frame():
+    d = _run(["--steps", "2", "--warmup", "1", "--height", "270", "--width", "480"])
+    for k in REQUIRED + ["roofline", "cpu_baseline", "clocks"]:
+        assert k in d, k
+    assert d["metric"] == "geodesic_steps_per_s" and d["unit"] == "steps/s" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["n_gpus"] == 1 and d["gpu_launches"] == 2 and d["value"] > 1e9 and d["e2e"]["value"] > 1e9
+    assert d["e2e"]["h2d_bytes_per_step"] == 270 * 480 * 3 and d["e2e"]["d2h_bytes_per_step"] == 270 * 480 * 4
+    r = d["roofline"]
+    assert r["bound"] == "fp64" and r["unit"] == "TFLOP/s" and 20 < r["peak"] < 45 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 1e5 and "rows" in c["sample"]
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_bench_reference_arm_small_frame():
+    """`--impl reference` = the oracle port on the host cores (CPU-only; also runs in the build container)."""
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--height", "54", "--width", "96"])
+    for k in REQUIRED + ["cpu_baseline", "impl"]:
+        assert k in d, k
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]

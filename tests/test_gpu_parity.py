@@ -370,3 +370,21 @@ def test_render_4k_rows_vs_oracle(handle, orc):
         nb = (ref["cls"].reshape(-1) != 0) & ~in_band_g(ref["ic"][:, 0:4])
         assert np.array_equal(sub["nsteps"][nb], ref["nsteps"][nb])
         assert state_close(sub["final_q"][nb], ref["final_q"][nb]).all()
+
+
+def test_integrate_batch_rows_equals_decimated_full(handle):
+    """N3: the decimated entry point returns exactly the rows np.linspace picks from integrate_batch_full."""
+    q0s, p0s = random_rays(33, seed=21)
+    steps, delta, rs, r_max, omega = 5000, 0.05, 2.0, 45.0, 1.0
+    full, rows_full = handle.integrate_batch_full(q0s, p0s, steps, delta, rs, r_max, omega, want_rows=True)
+    keep = np.linspace(0, steps - 1, num=1000, dtype=np.int32)
+    dec, rows = handle.integrate_batch_rows(q0s, p0s, steps, delta, rs, r_max, omega, keep, want_rows=True)
+    assert dec.shape == (33, 1000, 4)
+    assert np.array_equal(rows, rows_full)
+    assert np.array_equal(dec, full[:, keep, :], equal_nan=True)
+    # arbitrary ascending lists, the empty list, and the error path
+    keep2 = np.array([0, 1, 2, 7, 4999], np.int32)
+    assert np.array_equal(handle.integrate_batch_rows(q0s, p0s, steps, delta, rs, r_max, omega, keep2), full[:, keep2, :], equal_nan=True)
+    assert handle.integrate_batch_rows(q0s, p0s, steps, delta, rs, r_max, omega, np.zeros(0, np.int32)).shape == (33, 0, 4)
+    with pytest.raises(ValueError):
+        handle.integrate_batch_rows(q0s, p0s, steps, delta, rs, r_max, omega, np.array([3, 3], np.int32))
