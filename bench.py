@@ -284,6 +284,12 @@ def main():
                          "traffic": ncu.get("dram_bytes_per_launch") if world == 1 else None,
                          "traffic_unit": "bytes of DRAM read+write per launch (ncu --set full, " + ncu.get("source", "n/a") + ")",
                          "fp64_pipe_pct_of_peak_ncu": ncu.get("fp64_pipe_pct"),
+                         "executed_flop_per_step_ncu": ncu.get("executed_flop_per_step"),
+                         "executed_tflops": (ncu["executed_flop_per_step"] * steps_per_frame_local / (kern_ms[-1] * 1e-3) / 1e12
+                                             if "executed_flop_per_step" in ncu else None),
+                         "note": "achieved counts the reference's ALGORITHMIC work (312 flop/step: 4 flow evaluations, 36 divisions, "
+                                 "8 sin/cos per step); the kernel executes ~173 flop/step (3 flow evaluations, 3 reciprocals, memoised "
+                                 "trig), so frac can exceed 1 -- pipe utilisation is fp64_pipe_pct_of_peak_ncu",
                          "algorithmic_bytes_per_launch": 7 * h * w,
                          "peak_source": "measured in this run (schw_fp64_peak_probe: register-resident DFMA chains); "
                                         f"nominal {NOMINAL_FP64_TFLOPS} TFLOP/s",
