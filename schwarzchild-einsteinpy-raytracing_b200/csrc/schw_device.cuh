@@ -159,7 +159,7 @@ __device__ __forceinline__ void sincos_flow(double x, double &s, double &c)
 struct TrigMemo {
     double th;     // the angle the entry was computed for (compared bitwise)
     double is;     // 1 / sin(th)
-    double cis;    // cos(th) / sin(th)
+    double hcis;   // hh * cos(th) / sin(th), hh = the (fixed) step of the flow this entry serves
 };
 
 // The two trig-derived factors a flow needs: 1/sin(th) and cos(th)/sin(th).
@@ -178,16 +178,22 @@ __device__ __forceinline__ void flow(double r, double th,
                                      double &Qt, double &Qr, double &Qh, double &Qp,  // positions updated
                                      double hh, double hrs, double rs, TrigMemo &m)   // hrs = hh*rs
 {
-    double is, cis;
+    double is, hcis;
     if (kMemo) {
+        // NB: a memo entry serves ONE flow with ONE step size (m1: A(delta), m2: B(delta/2)); full-mask vote =>
+        // only call with kMemo from convergent code
         const bool same = __double_as_longlong(th) == __double_as_longlong(m.th);
         if (!__all_sync(0xffffffffu, same)) {
-            trig_factors(th, m.is, m.cis);
+            double cis;
+            trig_factors(th, m.is, cis);
+            m.hcis = hh * cis;
             m.th = th;
         }
-        is = m.is; cis = m.cis;
+        is = m.is; hcis = m.hcis;
     } else {
+        double cis;
         trig_factors(th, is, cis);
+        hcis = hh * cis;
     }
     const double d   = r - rs;
     const double R   = fast_rcp(r * d);          // 1 / (r (r - rs))
@@ -203,9 +209,8 @@ __device__ __forceinline__ void flow(double r, double th,
     double dHr = A1 * A1;
     dHr = fma(A2, A2, dHr);
     dHr = fma(-ir, e, dHr);
-    const double dHh = -cis * k;                 // -cos/sin^3 * pph^2 / r^2
     Pr = fma(-hh, dHr, Pr);
-    Ph = fma(-hh, dHh, Ph);
+    Ph = fma(hcis, k, Ph);                       // - hh dH/dth,  dH/dth = -cos/sin^3 pph^2 / r^2
     Qt = fma(-hh, r * A1, Qt);
     Qr = fma(-hrs, A2, fma(hh, pr, Qr));         // + hh (1 - rs/r) pr
     Qh = fma(hh, ir * A3, Qh);
@@ -229,11 +234,13 @@ struct Memo2 {
     TrigMemo m1, m2;      // for theta of copy 1 (flow A) and copy 2 (flow B)
     // start from a consistent entry (theta = the double nearest pi/2, where parked lanes and every
     // camera ray live); the memo is keyed by the angle's bits, so it can never go stale
-    __device__ __forceinline__ void invalidate()
+    __device__ __forceinline__ void init(double hA, double hB)
     {
-        m1.th = 1.5707963267948966;
-        trig_factors(m1.th, m1.is, m1.cis);
-        m2 = m1;
+        double cis;
+        m1.th = m2.th = 1.5707963267948966;
+        trig_factors(m1.th, m1.is, cis);
+        m2.is = m1.is;
+        m1.hcis = hA * cis; m2.hcis = hB * cis;
     }
 };
 
@@ -256,7 +263,8 @@ __device__ __forceinline__ void flow_C(RayState &S, double g, double hs)
 }
 
 // B(d/2) C(d) B(d/2): the part of _fantasy_step_ord2 (cuda_geodesic.py:569-575) between the two
-// A half-flows.  After it q1 is final for this step (the trailing A does not touch q1).
+// A half-flows.  After it q1 is final for this step (the trailing A does not touch q1), so the
+// termination test may equally be made after the merged A(d) that follows.
 template <bool kMemo>
 __device__ __forceinline__ void step_BCB(RayState &S, const StepParams &P, Memo2 &M)
 {

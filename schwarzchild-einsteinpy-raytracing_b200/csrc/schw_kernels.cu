@@ -148,10 +148,10 @@ struct RenderJob {
 // The persistent ray kernel.
 //
 // Loop structure per lane (reference: fantasy_integrate_batch_ord2, cuda_geodesic.py:579-602):
-//     fetch ray -> [test] A(hA) B(h) C(d) B(h) [count, test] A(hA) B C B [test] ...
-// where hA = d/2 for the first flow of a fresh ray and d afterwards (merged trailing+leading A).
-// All 32 lanes execute the same A,B,C,B sequence; only the refill/epilogue is divergent and it
-// runs once per ray (~0.03 % of a ray's work).
+//     fetch ray -> [test] A(d/2) | B(d/2) C(d) B(d/2) A(d) [count, test] | B C B A(d) [test] | ...
+// A(d) = the trailing A(d/2) of one step merged with the leading A(d/2) of the next (A does not touch q1, so the
+// test on q1 may follow it; the A applied after a ray's last step is discarded with the rest of its state).
+// All 32 lanes execute the same B,C,B,A sequence; only the service (epilogue + refill) is divergent.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void park(RayState &S, const StepParams &P)
 {
@@ -174,10 +174,9 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     const unsigned lane = threadIdx.x & 31u;
     RayState S;
     Memo2 M;
-    M.invalidate();
+    M.init(P.delta, P.h);        // m1 serves the merged A(delta) of the step loop, m2 the two B(delta/2)
     int k = -1;                  // ray in flight, or finished ray awaiting service (n < 2^31 is checked on the host)
     int n = 0;                   // steps taken by the ray in flight
-    bool fresh = false;
     bool active = false;         // integrating a ray
     bool waiting = false;        // ray finished: result parked in shared memory, epilogue + refill pending
     bool drained = false;        // queue is empty
@@ -220,7 +219,10 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
                             job.store(kk, S.q1t, S.q1r, S.q1h, S.q1p, 0, false, slot);
                             park(S, P);
                         } else {
-                            k = kk; n = 0; active = true; fresh = true;
+                            // leading A(d/2) of the ray's first step (cuda_geodesic.py:571); every later A is the merged
+                            // trailing+leading A(d) at the end of the loop body.  Divergent code: no memo vote here.
+                            flow_A<false>(S, P.h, P.h_rs, P.rs, M);
+                            k = kk; n = 0; active = true;
                         }
                     }
                 } else {
@@ -233,11 +235,8 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
 
         // ---- integrate; finished lanes park their result and idle until servicing them pays ----
         while (true) {
-            const double hA = fresh ? P.h : P.delta;
-            const double hArs = fresh ? P.h_rs : P.d_rs;
-            fresh = false;
-            flow_A<kMemo>(S, hA, hArs, P.rs, M);
-            step_BCB<kMemo>(S, P, M);
+            step_BCB<kMemo>(S, P, M);                               // q1 is now final for this step
+            flow_A<kMemo>(S, P.delta, P.d_rs, P.rs, M);             // trailing A(d/2) + next step's leading A(d/2)
             ++n; ++it;
             const bool done = active && (n >= P.steps || finished_or_nan(S.q1r, P));
             const bool any_done = __any_sync(kFull, done);
@@ -331,8 +330,7 @@ integrate_rows_kernel(const double *__restrict__ q0s, const double *__restrict__
         const double p0[4] = {p0s[4 * i], p0s[4 * i + 1], p0s[4 * i + 2], p0s[4 * i + 3]};
         init_state(S, q0, p0);
     }
-    Memo2 M;
-    M.invalidate();
+    Memo2 M;      // unused (kMemo = false): lanes of this kernel leave the loop at different times
     double2 *row = reinterpret_cast<double2 *>(out + (size_t)i * (size_t)nidx * 4);
     int cur = 0;
     int next = nidx > 0 ? row_idx[0] : -1;
@@ -358,9 +356,9 @@ integrate_rows_kernel(const double *__restrict__ q0s, const double *__restrict__
             rows = P.steps;
             break;
         }
-        flow_A<true>(S, fresh ? P.h : P.delta, fresh ? P.h_rs : P.d_rs, P.rs, M);
+        flow_A<false>(S, fresh ? P.h : P.delta, fresh ? P.h_rs : P.d_rs, P.rs, M);
         fresh = false;
-        step_BCB<true>(S, P, M);
+        step_BCB<false>(S, P, M);
     }
     if (out_rows) out_rows[i] = rows;
     atomicAdd(&ctr->total_steps, (unsigned long long)(rows > 0 ? rows - 1 : 0));
