@@ -33,7 +33,7 @@ namespace schw {
 #define SCHW_BLOCK 128
 #endif
 #ifndef SCHW_MINBLOCKS
-#define SCHW_MINBLOCKS 6
+#define SCHW_MINBLOCKS 5
 #endif
 constexpr int kBlock = SCHW_BLOCK;   // threads per CTA (tuning variants: make VARIANT_FLAGS=-DSCHW_BLOCK=.. OUT=..)
 constexpr unsigned kFull = 0xffffffffu;
