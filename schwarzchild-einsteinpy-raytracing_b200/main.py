@@ -18,8 +18,23 @@ from simulation.utils import _apply_relative_offsets  # noqa: E402
 logging.basicConfig(level=logging.INFO, format='%(asctime)s %(levelname)s: %(message)s')
 
 
+def _init_distributed():
+    """Under torchrun (WORLD_SIZE > 1): one process per GPU; rows are sharded by simulation.raytracing / schw_b200.multigpu."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank()
+
+
 def main(argv=None):
     args = parse_args(argv)
+    rank = _init_distributed()
     image_size = (args.height or args.size, args.width or args.size)
     bh = BlackHole(mass=args.bh_mass)
     observer = Observer(position=np.array([args.observer_distance, 0, 0]), fov=np.radians(args.fov), image_size=image_size)
@@ -31,7 +46,7 @@ def main(argv=None):
 
     logging.info("Saving no-gravity image using background...")
     flat_trajectories = None
-    if not args.no_flat_trajectories:
+    if not args.no_flat_trajectories and rank == 0:
         flat_trajectories = save_no_gravity_image_with_background(
             observer, args.background, 'images/no_gravity.png', boundary_radius=args.boundary_radius,
             return_sampled_trajectories=True, n_sampled=10, override_patch_center=False, **patch)
@@ -42,6 +57,8 @@ def main(argv=None):
         suppress_warnings=args.suppress_warnings, background_path=args.background, use_cuda=args.cuda,
         boundary_radius=args.boundary_radius, n_samples=20, **patch)
     img, photon_trajectories = result if isinstance(result, tuple) else (result, None)
+    if rank != 0:
+        return                                  # rank 0 owns the files and the summary
     _save_png('images/manual_output.png', img)
     logging.info("Saved manual_output.png")
 

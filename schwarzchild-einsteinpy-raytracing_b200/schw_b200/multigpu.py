@@ -23,6 +23,14 @@ def dist_info():
     return 0, 1
 
 
+def broadcast_object(obj, src=0):
+    """Small Python object from rank `src` to all ranks (host-side bookkeeping, e.g. the sampled pixel list)."""
+    import torch.distributed as dist
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def shard_rows(height, rank, world):
     """Rows of rank `rank`: (row_begin, row_end, row_stride) of the cyclic distribution."""
     return rank, height, world

@@ -78,6 +78,9 @@ def run_manual_simulation(
         import random
         while len(sampled_indices) < n_samples:           # unseeded draw like raytracing.py:44-48
             sampled_indices.add((random.randint(0, h - 1), random.randint(0, w - 1)))
+        from schw_b200.multigpu import dist_info, broadcast_object
+        if dist_info()[1] > 1:                            # every rank must agree on the sampled pixels
+            sampled_indices = set(broadcast_object(sorted(sampled_indices)))
     if not (n_samples > 0 and sampled_indices):
         # reference quirk (App. D-3): the whole image-building block is nested under this test
         print("Summary counts not available (CPU fallback mode).")
@@ -112,7 +115,8 @@ def run_manual_simulation(
         c, sn = np.cos(betas[flat]), np.sin(betas[flat])
         sampled_traj_data.append(np.stack([x, c * y - sn * z, sn * y + c * z], axis=1).astype(np.float64))
 
-    if write_outputs:
+    from schw_b200.multigpu import dist_info
+    if write_outputs and dist_info()[0] == 0:           # under torchrun only rank 0 writes the files
         import pandas as pd
         _save_png('images/manual_output.png', img)
         logging.info("Saved manual_output.png")

@@ -388,3 +388,42 @@ def test_integrate_batch_rows_equals_decimated_full(handle):
     assert handle.integrate_batch_rows(q0s, p0s, steps, delta, rs, r_max, omega, np.zeros(0, np.int32)).shape == (33, 0, 4)
     with pytest.raises(ValueError):
         handle.integrate_batch_rows(q0s, p0s, steps, delta, rs, r_max, omega, np.array([3, 3], np.int32))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(obs=(30.0, 0, 0), fov=np.radians(60.0), height=48, width=64, mass=1.5, r_max=31.0, delta=0.05, steps=40000),    # quirk D-5: M != 1
+    dict(obs=(30.0, 0, 0), fov=np.radians(60.0), height=48, width=64, mass=0.75, r_max=31.0, delta=0.05, steps=40000),
+    dict(obs=(20.0, 0, 0), fov=np.radians(90.0), height=50, width=50, r_max=21.0, delta=0.05, steps=30000,
+         patch_size_theta=np.deg2rad(126), patch_size_phi=np.deg2rad(224), flip_phi=True),                              # test-band-axis.py scene
+    dict(obs=(30.0, 0, 0), height=40, width=60, delta=0.05, patch_center_phi=np.deg2rad(217.0), patch_center_theta=np.deg2rad(80.0),
+         patch_size_theta=np.deg2rad(60), patch_size_phi=np.deg2rad(90), flip_theta=True),                              # sweep-style relobs offset
+    dict(obs=(30.0, 0, 0), height=33, width=65, delta=0.05, omega=0.01),                                               # integrator with small omega
+    dict(obs=(30.0, 0, 0), height=32, width=32, delta=0.05, has_texture=False),                                         # background_path=None
+    dict(obs=(30.0, 0, 0), height=32, width=32, delta=0.05, steps=300),                                                 # step cap: in_domain
+])
+def test_render_other_scenes_vs_oracle(handle, orc, kw):
+    import schw_b200
+    h, w = kw["height"], kw["width"]
+    tex = synthetic_sky(h, w, 12) if kw.get("has_texture", True) else None
+    got = handle.render(schw_b200.make_scene(**kw), tex, extras=True)
+    ref = orc.render(orc.make_scene(**kw), tex)
+    assert ref["rc"] == 0
+    full = dict(patch_center_theta=np.pi / 2, patch_center_phi=np.pi, patch_size_theta=np.pi, patch_size_phi=2 * np.pi,
+                flip_theta=False, flip_phi=False)
+    full.update(kw)
+    # rays whose reference result is ill-conditioned may legitimately change class; everything else is bit-exact
+    sc = orc.make_scene(**kw)
+    q0 = np.tile(np.array([0.0, np.hypot(*kw["obs"][:2]), np.pi / 2, 0.0]), (h * w, 1))
+    cond = orc.conditioning(q0, ref["ic"][:, :4].copy(), sc.steps, sc.delta, 2 * sc.mass, sc.r_max, sc.omega)
+    ok = (cond <= COND_MAX) & ~in_band_g(ref["ic"][:, :4], mass=sc.mass)
+    assert ok.mean() > 0.6
+    masked = ref["cls"].reshape(-1) == 0                        # forced to 'bh' by the analytic mask whatever the integrator did
+    good = ok | masked
+    assert np.array_equal(got["cls"].reshape(-1)[good], ref["cls"].reshape(-1)[good])
+    assert (got["cls"].reshape(-1) != ref["cls"].reshape(-1)).mean() < 0.01
+    fu, fv = texel_coords(full, ref["hit"][:, 0], ref["hit"][:, 1])
+    diff = np.any(got["rgb"].reshape(-1, 3) != ref["rgb"].reshape(-1, 3), axis=1) & good
+    assert np.all(near_rounding_boundary(fu, fv)[diff])
+    sel = ok & ~masked
+    assert np.array_equal(got["nsteps"][sel], ref["nsteps"][sel])
+    assert state_close(got["final_q"][sel], ref["final_q"][sel]).all(), relerr(got["final_q"][sel], ref["final_q"][sel], 1.0).max()
