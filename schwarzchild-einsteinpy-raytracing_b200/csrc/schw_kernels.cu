@@ -591,7 +591,7 @@ extern "C" int schw_create(int device, schw_handle **out)
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     CU(cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device));
-    strncpy(h->name, prop.name, sizeof(h->name) - 1);
+    snprintf(h->name, sizeof(h->name), "%s", prop.name);
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
