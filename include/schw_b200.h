@@ -151,6 +151,11 @@ int  schw_render_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_t
 /* Sum of integrator steps over the rays of the last schw_render* / schw_integrate_batch* call on
  * this handle (device-side counter; used for the steps/s metric). */
 int  schw_last_total_steps(schw_handle *h, uint64_t *total_steps);
+/* Loop statistics of the same call (any pointer may be NULL): total_steps as above; warp_iters = step-loop bodies
+ * executed summed over warps (total_steps / (32 * warp_iters) = fraction of issued lane-steps that advanced a ray,
+ * the rest being lanes that idle between a ray's end and the next refill); planar_iters = how many of those bodies
+ * ran entirely on the equatorial fast path (csrc/schw_device.cuh "Planar steps").  Zero for the trajectory kernels. */
+int  schw_last_counters(schw_handle *h, uint64_t *total_steps, uint64_t *warp_iters, uint64_t *planar_iters);
 
 /* ---- next rows: flat-space comparison render ----------------------------------
  * Replaces the pixel loop of save_no_gravity_image_with_background (simulation/background.py:

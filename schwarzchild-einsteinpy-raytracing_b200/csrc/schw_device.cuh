@@ -31,6 +31,15 @@ struct StepParams {
     double rcap;     // 1.1*rs evaluated in FP64           (cuda_geodesic.py:598)
     double r_max;
     double mg, mhs;  // (1-cos(2 w d))/2, sin(2 w d)/2   (cuda_geodesic.py:545-546; cos/sin from host libm)
+    // equatorial fast path (see "Planar steps" below); thresholds are compared on the high 32 bits of a double
+    double pl_hcA, pl_hcB;   // delta * cot(th_eq), (delta/2) * cot(th_eq), th_eq = the double nearest pi/2
+    double pl_zero_hs;       // (+0) * mhs: the signed zero the mixed flow adds to p_theta when q1_theta == q2_theta
+    int32_t pl_enable;
+    int32_t pl_ph_hi;        // |p_theta| <  T      <=  hi(|p_theta|) <  pl_ph_hi
+    int32_t pl_r_hi;         // r         >= r_thr  <=  hi(r)         >= pl_r_hi   (signed compare)
+    int32_t pl_pp_hi;        // |p_phi|   >  2^28 T <=  hi(|p_phi|)   >= pl_pp_hi
+    // termination pre-test on the high word of r (integer pipe): hi(r) > hi_rcap && hi(r) < hi_rmax  =>  rcap < r < r_max
+    int32_t hi_rcap, hi_rmax;
     int32_t steps;
     int32_t _pad;
 };
@@ -171,6 +180,56 @@ __device__ __forceinline__ void trig_factors(double th, double &is, double &cis)
     cis = c * is;
 }
 
+// The part of a flow that does not involve theta or the angular momenta: reciprocals, dt/dl, dr/dl, and the (t,r)
+// terms of dH/dr.  Shared by the general and the planar tail below (the same operations in the same order as one
+// monolithic flow, so splitting changes no result bit); it also gives the warp votes that choose the tail ~40 cycles
+// of independent FP64 work to resolve behind.
+struct FlowHead {
+    double ir;     // 1 / r
+    double dH0;    // (pt/(r-rs))^2 + (pr/r)^2
+};
+__device__ __forceinline__ FlowHead flow_head(double r, double pt, double pr, double &Qt, double &Qr,
+                                              double hh, double hrs, double rs)
+{
+    const double d   = r - rs;
+    const double R   = fast_rcp(r * d);          // 1 / (r (r - rs))
+    FlowHead f;
+    f.ir = R * d;                                // 1 / r
+    const double id  = R * r;                    // 1 / (r - rs)
+    const double A1  = id * pt;
+    const double A2  = f.ir * pr;
+    f.dH0 = fma(A2, A2, A1 * A1);
+    Qt = fma(-hh, r * A1, Qt);
+    Qr = fma(-hrs, A2, fma(hh, pr, Qr));         // + hh (1 - rs/r) pr
+    return f;
+}
+
+// Warp-uniform refresh of a memo entry (must be called convergently).
+__device__ __forceinline__ void memo_refresh(double th, double hh, TrigMemo &m)
+{
+    const bool same = __double_as_longlong(th) == __double_as_longlong(m.th);
+    if (!__all_sync(0xffffffffu, same)) {
+        double cis;
+        trig_factors(th, m.is, cis);
+        m.hcis = hh * cis;
+        m.th = th;
+    }
+}
+
+__device__ __forceinline__ void flow_tail(const FlowHead &f, double ph, double pp, double is, double hcis,
+                                          double &Pr, double &Ph, double &Qh, double &Qp, double hh)
+{
+    const double A3  = f.ir * ph;
+    const double w   = f.ir * is;                // 1 / (r sin th)
+    const double A4  = w * pp;
+    const double k   = A4 * A4;
+    const double e   = fma(A3, A3, k);
+    Pr = fma(-hh, fma(-f.ir, e, f.dH0), Pr);
+    Ph = fma(hcis, k, Ph);                       // - hh dH/dth,  dH/dth = -cos/sin^3 pph^2 / r^2
+    Qh = fma(hh, f.ir * A3, Qh);
+    Qp = fma(hh, w * A4, Qp);
+}
+
 template <bool kMemo>
 __device__ __forceinline__ void flow(double r, double th,
                                      double pt, double pr, double ph, double pp,
@@ -182,39 +241,15 @@ __device__ __forceinline__ void flow(double r, double th,
     if (kMemo) {
         // NB: a memo entry serves ONE flow with ONE step size (m1: A(delta), m2: B(delta/2)); full-mask vote =>
         // only call with kMemo from convergent code
-        const bool same = __double_as_longlong(th) == __double_as_longlong(m.th);
-        if (!__all_sync(0xffffffffu, same)) {
-            double cis;
-            trig_factors(th, m.is, cis);
-            m.hcis = hh * cis;
-            m.th = th;
-        }
+        memo_refresh(th, hh, m);
         is = m.is; hcis = m.hcis;
     } else {
         double cis;
         trig_factors(th, is, cis);
         hcis = hh * cis;
     }
-    const double d   = r - rs;
-    const double R   = fast_rcp(r * d);          // 1 / (r (r - rs))
-    const double ir  = R * d;                    // 1 / r
-    const double id  = R * r;                    // 1 / (r - rs)
-    const double A1  = id * pt;
-    const double A2  = ir * pr;
-    const double A3  = ir * ph;
-    const double w   = ir * is;                  // 1 / (r sin th)
-    const double A4  = w * pp;
-    const double k   = A4 * A4;
-    const double e   = fma(A3, A3, k);
-    double dHr = A1 * A1;
-    dHr = fma(A2, A2, dHr);
-    dHr = fma(-ir, e, dHr);
-    Pr = fma(-hh, dHr, Pr);
-    Ph = fma(hcis, k, Ph);                       // - hh dH/dth,  dH/dth = -cos/sin^3 pph^2 / r^2
-    Qt = fma(-hh, r * A1, Qt);
-    Qr = fma(-hrs, A2, fma(hh, pr, Qr));         // + hh (1 - rs/r) pr
-    Qh = fma(hh, ir * A3, Qh);
-    Qp = fma(hh, w * A4, Qp);
+    const FlowHead f = flow_head(r, pt, pr, Qt, Qr, hh, hrs, rs);
+    flow_tail(f, ph, pp, is, hcis, Pr, Ph, Qh, Qp, hh);
 }
 
 // _flow_mixed_dev, cuda_geodesic.py:528-566, for one component.  With g = (1-cos)/2, hs = sin/2:
@@ -227,6 +262,45 @@ __device__ __forceinline__ void mix(double &q1, double &p1, double &q2, double &
     const double w = fma(qd, g, -(pd * hs));
     const double z = fma(pd, g, qd * hs);
     q1 -= w; q2 += w;
+    p1 -= z; p2 += z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Planar steps.  Every camera ray of the reference starts at theta = th_eq (the double nearest pi/2)
+// with p_theta = -0.0 (utils.py:129,172).  cot(th_eq) = 6.1e-17 then feeds p_theta a few 1e-19 per
+// flow, which never moves theta off th_eq: the theta sector only *receives*.  While the following
+// holds for every lane of the warp, the theta terms of a flow are provably no-ops in FP64 and are
+// skipped (7 of 27 FP64 instructions per flow, 6 of 40 in the mixed flow), bit for bit:
+//   (R0) both copies have theta == th_eq bitwise   => 1/sin = 1.0 exactly, cot = 6.123233995736766e-17
+//   (R1) hh |p_th| / r^2 <= 2^-54                   => theta + hh g^thth p_th rounds back to theta (ulp(th_eq)/2 = 2^-53)
+//   (R2) |p_th| <= 2^-28 |p_ph|                     => fma(A3, A3, k) == k in dH/dr    (A3 = p_th/r, k = (p_ph/r)^2)
+//   (R3) 2 T |hs| <= 2^-54 with |p_th| < T          => the mixed flow's w = -(p1_th - p2_th) hs leaves both thetas alone
+// (R1)-(R3) follow from |p_th| < T, r >= r_thr, |p_ph| >= 2^28 T with T, r_thr chosen on the host
+// (make_step_params); they are tested with integer compares on the high words, which do not occupy
+// the FP64 pipe.  p_theta itself is still integrated exactly, so a warp can leave the fast path at any
+// sub-step (a high-winding ray whose p_theta outgrows T, a ray loaded with a different theta, ...) and
+// continue with the general flow.  B#2 needs no p_theta test: the mixed flow with q1_th == q2_th is a
+// convex combination of p1_th and p2_th (0 <= g <= 1).  Results are bit-identical with SCHW_PLANAR=0.
+// Every flow is split into a theta-independent head and a general / planar tail (flow_head, flow_tail*).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7fffffff; }
+__device__ __forceinline__ bool is_th_eq(double th) { return __double_as_longlong(th) == 0x3FF921FB54442D18LL; }
+
+__device__ __forceinline__ void flow_tail_planar(const FlowHead &f, double pp, double hc,
+                                                 double &Pr, double &Ph, double &Qp, double hh)
+{
+    const double A4  = f.ir * pp;                // w = ir * (1/sin) = ir * 1.0
+    const double k   = A4 * A4;
+    Pr = fma(-hh, fma(-f.ir, k, f.dH0), Pr);     // e = fma(A3, A3, k) == k by (R2)
+    Ph = fma(hc, k, Ph);
+    Qp = fma(hh, f.ir * A4, Qp);
+}
+
+// theta component of the mixed flow when q1_th == q2_th and (R3): only the momenta move.
+__device__ __forceinline__ void mix_planar(double &p1, double &p2, double g, double zero_hs)
+{
+    const double pd = p1 - p2;
+    const double z = fma(pd, g, zero_hs);
     p1 -= z; p2 += z;
 }
 
@@ -262,6 +336,59 @@ __device__ __forceinline__ void flow_C(RayState &S, double g, double hs)
     mix(S.q1p, S.p1p, S.q2p, S.p2p, g, hs);
 }
 
+// One full loop body B(d/2) C(d) B(d/2) A(d) with the planar fast path.
+//   tok    (warp-uniform, carried by the caller): (R0) and the tests of the first B held for every lane when the
+//          previous step ended; the caller clears it whenever lanes were given new rays.
+//   pp_hi  this lane's |p_phi| threshold: P.pl_pp_hi while it integrates a ray, 0 while it is parked (parked lanes sit
+//          on the fixed point p = 0, theta = th_eq, where both variants of every flow are the identity and every other
+//          test passes by itself).
+// Each vote is issued as soon as its inputs exist and consumed only after the next flow_head, so its latency hides
+// behind independent FP64 work.  Returns whether the whole step ran on the fast path.  Must be called convergently.
+__device__ __forceinline__ bool step_BCBA_planar(RayState &S, const StepParams &P, Memo2 &M, int pp_hi, bool &tok)
+{
+    constexpr unsigned kFullMask = 0xffffffffu;
+    const int T = P.pl_ph_hi, RT = P.pl_r_hi;
+    if (!tok)       // after a refill, or while some lane carries a ray with polar motion
+        tok = __all_sync(kFullMask, is_th_eq(S.q1h) & is_th_eq(S.q2h) &
+                                    (hi_abs(S.p1h) < T) & (__double2hiint(S.q2r) >= RT) & (hi_abs(S.p1p) >= pp_hi));
+    // ---- B(d/2): reads (q2, p1), writes p2 and q1 ----
+    const bool v1 = tok;
+    FlowHead f = flow_head(S.q2r, S.p1t, S.p1r, S.q1t, S.q1r, P.h, P.h_rs, P.rs);
+    if (__builtin_expect(v1, 1)) {
+        flow_tail_planar(f, S.p1p, P.pl_hcB, S.p2r, S.p2h, S.q1p, P.h);
+    } else {
+        memo_refresh(S.q2h, P.h, M.m2);
+        flow_tail(f, S.p1h, S.p1p, M.m2.is, M.m2.hcis, S.p2r, S.p2h, S.q1h, S.q1p, P.h);
+    }
+    // ---- C(d), and the tests of the second B (its r and p_phi are final once their components are mixed) ----
+    mix(S.q1r, S.p1r, S.q2r, S.p2r, P.mg, P.mhs);
+    mix(S.q1p, S.p1p, S.q2p, S.p2p, P.mg, P.mhs);
+    const bool v2 = __all_sync(kFullMask, v1 & (hi_abs(S.p2h) < T) & (__double2hiint(S.q2r) >= RT) & (hi_abs(S.p1p) >= pp_hi));
+    mix(S.q1t, S.p1t, S.q2t, S.p2t, P.mg, P.mhs);
+    if (__builtin_expect(v2, 1)) mix_planar(S.p1h, S.p2h, P.mg, P.pl_zero_hs);
+    else mix(S.q1h, S.p1h, S.q2h, S.p2h, P.mg, P.mhs);
+    // ---- B(d/2) ----
+    f = flow_head(S.q2r, S.p1t, S.p1r, S.q1t, S.q1r, P.h, P.h_rs, P.rs);
+    if (__builtin_expect(v2, 1)) {
+        flow_tail_planar(f, S.p1p, P.pl_hcB, S.p2r, S.p2h, S.q1p, P.h);
+    } else {
+        memo_refresh(S.q2h, P.h, M.m2);
+        flow_tail(f, S.p1h, S.p1p, M.m2.is, M.m2.hcis, S.p2r, S.p2h, S.q1h, S.q1p, P.h);
+    }
+    // ---- A(d): reads (q1, p2), writes p1 and q2 ----
+    const bool v4 = __all_sync(kFullMask, v2 & (hi_abs(S.p2h) < T) & (__double2hiint(S.q1r) >= RT) & (hi_abs(S.p2p) >= pp_hi));
+    f = flow_head(S.q1r, S.p2t, S.p2r, S.q2t, S.q2r, P.delta, P.d_rs, P.rs);
+    if (__builtin_expect(v4, 1)) {
+        flow_tail_planar(f, S.p2p, P.pl_hcA, S.p1r, S.p1h, S.q2p, P.delta);
+    } else {
+        memo_refresh(S.q1h, P.delta, M.m1);
+        flow_tail(f, S.p2h, S.p2p, M.m1.is, M.m1.hcis, S.p1r, S.p1h, S.q2h, S.q2p, P.delta);
+    }
+    // the next step's first B: its inputs (p1_th, q2_r, p1_ph) are final now
+    tok = __all_sync(kFullMask, v4 & (hi_abs(S.p1h) < T) & (__double2hiint(S.q2r) >= RT) & (hi_abs(S.p1p) >= pp_hi));
+    return v4;
+}
+
 // B(d/2) C(d) B(d/2): the part of _fantasy_step_ord2 (cuda_geodesic.py:569-575) between the two
 // A half-flows.  After it q1 is final for this step (the trailing A does not touch q1), so the
 // termination test may equally be made after the merged A(d) that follows.
@@ -278,6 +405,14 @@ __device__ __forceinline__ void step_BCB(RayState &S, const StepParams &P, Memo2
 __device__ __forceinline__ bool terminated(double r, const StepParams &P)
 {
     return (r <= P.rcap) || (r >= P.r_max);
+}
+// Cheap necessary condition for the test below, on the high 32 bits of r only (two integer compares instead of two
+// FP64 compares per step): when it is false the ray is certainly still strictly inside (rcap, r_max).  The host sets
+// hi_rcap / hi_rmax so that this holds for every r, inf and NaN included (make_step_params).
+__device__ __forceinline__ bool maybe_finished(double r, const StepParams &P)
+{
+    const int hr = __double2hiint(r);
+    return !((hr > P.hi_rcap) & (hr < P.hi_rmax));
 }
 // "not strictly inside (rcap, r_max)": the same test with NaN counted as finished (two compares).
 __device__ __forceinline__ bool finished_or_nan(double r, const StepParams &P)

@@ -33,7 +33,13 @@ namespace schw {
 #define SCHW_BLOCK 128
 #endif
 #ifndef SCHW_MINBLOCKS
-#define SCHW_MINBLOCKS 5
+#define SCHW_MINBLOCKS 6
+#endif
+#ifndef SCHW_MINBLOCKS_GENERAL
+#define SCHW_MINBLOCKS_GENERAL 5     // kernels without the planar fast path keep the trig memo in registers (94 of them)
+#endif
+#ifndef SCHW_MEMO_SMEM
+#define SCHW_MEMO_SMEM 1
 #endif
 constexpr int kBlock = SCHW_BLOCK;   // threads per CTA (tuning variants: make VARIANT_FLAGS=-DSCHW_BLOCK=.. OUT=..)
 constexpr unsigned kFull = 0xffffffffu;
@@ -41,6 +47,8 @@ constexpr unsigned kFull = 0xffffffffu;
 struct Counters {
     unsigned long long next;         // ray queue head
     unsigned long long total_steps;  // integrator steps executed
+    unsigned long long warp_iters;   // loop bodies executed, summed over warps (32 x this = lane-steps issued)
+    unsigned long long planar_iters; // of those, completed entirely on the planar fast path
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -159,8 +167,8 @@ __device__ __forceinline__ void park(RayState &S, const StepParams &P)
     init_state(S, q0, p0);
 }
 
-template <class Job, bool kMemo>
-__global__ void __launch_bounds__(kBlock, SCHW_MINBLOCKS)
+template <class Job, bool kMemo, bool kPlanar>
+__global__ void __launch_bounds__(kBlock, kPlanar ? SCHW_MINBLOCKS : SCHW_MINBLOCKS_GENERAL)
 persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepParams P, Counters *ctr)
 {
     __shared__ double2 s_slot[kBlock];        // (alpha0, beta) of the ray in flight, for its epilogue
@@ -173,7 +181,14 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     double2 &slot = s_slot[threadIdx.x];
     const unsigned lane = threadIdx.x & 31u;
     RayState S;
+#if SCHW_MEMO_SMEM
+    // On the planar fast path the trig memo is not touched, so it can live in shared memory (12 registers less).
+    __shared__ Memo2 s_memo[kPlanar ? kBlock : 1];
+    Memo2 M_reg;
+    Memo2 &M = kPlanar ? s_memo[threadIdx.x] : M_reg;
+#else
     Memo2 M;
+#endif
     M.init(P.delta, P.h);        // m1 serves the merged A(delta) of the step loop, m2 the two B(delta/2)
     int k = -1;                  // ray in flight, or finished ray awaiting service (n < 2^31 is checked on the host)
     int n = 0;                   // steps taken by the ray in flight
@@ -182,6 +197,9 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     bool drained = false;        // queue is empty
     int it = 0;                  // warp-uniform iteration counter
     int debt = 0;                // lane-steps spent idle by waiting lanes since the last service (warp-uniform)
+    bool tok = false;            // planar fast path: the next step may start on it (warp-uniform, see step_BCBA_planar)
+    int npl = 0;                 // iterations completed on the planar fast path (warp-uniform)
+    int pp_hi = 0;               // planar fast path: this lane's |p_phi| threshold (0 while parked)
 
     // Lanes without a ray sit on a fixed point of all three flows (p = 0 => dq = dH = 0, mixing of
     // equal copies is the identity), so they execute the same instructions without ever producing
@@ -232,16 +250,25 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
         }
         if (__ballot_sync(kFull, active) == 0u) break;             // every lane is out of work
         debt = 0;
+        tok = false;                                               // new rays on board: re-establish (R0)
+        pp_hi = active ? P.pl_pp_hi : 0;
 
         // ---- integrate; finished lanes park their result and idle until servicing them pays ----
         while (true) {
-            step_BCB<kMemo>(S, P, M);                               // q1 is now final for this step
-            flow_A<kMemo>(S, P.delta, P.d_rs, P.rs, M);             // trailing A(d/2) + next step's leading A(d/2)
+            if (kPlanar) {
+                npl += step_BCBA_planar(S, P, M, pp_hi, tok);
+            } else {
+                step_BCB<kMemo>(S, P, M);                           // q1 is now final for this step
+                flow_A<kMemo>(S, P.delta, P.d_rs, P.rs, M);         // trailing A(d/2) + next step's leading A(d/2)
+            }
             ++n; ++it;
-            const bool done = active && (n >= P.steps || finished_or_nan(S.q1r, P));
-            const bool any_done = __any_sync(kFull, done);
+            // termination (cuda_geodesic.py:598): a two-compare integer pre-test on the high word of r every step, the exact
+            // FP64 test only in the (rare) steps where some lane's pre-test cannot rule termination out
+            const bool maybe = active & ((n >= P.steps) | maybe_finished(S.q1r, P));
             const bool tick = (it & 15) == 0;
-            if (any_done || tick) {
+            if (__any_sync(kFull, maybe) || tick) {
+                const bool done = maybe && (n >= P.steps || finished_or_nan(S.q1r, P));
+                const bool any_done = __any_sync(kFull, done);
                 // idle cost so far: every waiting lane wastes one lane-step per iteration (booked every 16 iterations)
                 const unsigned wm = __ballot_sync(kFull, waiting);
                 if (tick) debt += __popc(wm) * 16;
@@ -250,7 +277,7 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
                     s_fin[kBlock + threadIdx.x] = make_double2(S.q1h, S.q1p);
                     s_nsteps[threadIdx.x] = n;
                     atomicAdd(&s_total, (unsigned long long)n);
-                    active = false; waiting = true;
+                    active = false; waiting = true; pp_hi = 0;
                     park(S, P);
                 }
                 // Service now if nobody is left integrating, or once the accumulated idle cost reaches the cost of
@@ -261,7 +288,11 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
         }
     }
 
-    // ---- total step count (metric numerator) ----
+    // ---- total step count (metric numerator) and loop statistics ----
+    if (lane == 0 && it) {
+        atomicAdd(&ctr->warp_iters, (unsigned long long)it);
+        if (npl) atomicAdd(&ctr->planar_iters, (unsigned long long)npl);
+    }
     __syncthreads();
     if (threadIdx.x == 0 && s_total) atomicAdd(&ctr->total_steps, s_total);
 }
@@ -543,7 +574,7 @@ struct schw_handle {
     bool timed = false;
     int launches = 0;
     Counters *ctr = nullptr;
-    int occ_render = 0, occ_batch = 0;
+    int occ_render[3] = {0, 0, 0}, occ_batch[3] = {0, 0, 0};   // filled on first use, see launch_persistent
     // grow-only scratch
     DevBuf in_a, in_b, in_c, tex, rgb, cls, fq, ic, hit, texel, nsteps, traj, rows, order;
     double order_key[12] = {0};   // camera geometry the cached tile order was built for
@@ -597,9 +628,6 @@ extern "C" int schw_create(int device, schw_handle **out)
     CU(cudaEventCreate(&h->ev1));
     CU(cudaMalloc(&h->ctr, sizeof(Counters)));
     CU(cudaMemset(h->ctr, 0, sizeof(Counters)));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_render, persistent_rays<RenderJob, true>, kBlock, 0));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->occ_batch, persistent_rays<BatchJob, true>, kBlock, 0));
-    if (h->occ_render < 1 || h->occ_batch < 1) return fail(SCHW_E_CUDA, "kernel does not fit on an SM");
     *out = h;
     return SCHW_OK;
 }
@@ -652,7 +680,64 @@ extern "C" int schw_last_total_steps(schw_handle *h, uint64_t *total_steps)
     return SCHW_OK;
 }
 
+extern "C" int schw_last_counters(schw_handle *h, uint64_t *total_steps, uint64_t *warp_iters, uint64_t *planar_iters)
+{
+    if (!h) return fail(SCHW_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    Counters c;
+    CU(cudaStreamSynchronize(h->last_stream ? h->last_stream : h->stream));
+    CU(cudaMemcpy(&c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost));
+    if (total_steps) *total_steps = c.total_steps;
+    if (warp_iters) *warp_iters = c.warp_iters;
+    if (planar_iters) *planar_iters = c.planar_iters;
+    return SCHW_OK;
+}
+
 // ---- parameter preparation (host FP64, glibc — the same libm NumPy uses for sin/cos) ------------
+// SCHW_PLANAR=0 disables the equatorial fast path (A/B measurements; results are bit-identical).
+// (The A/B switches are read on every call, so a test can flip them inside one process.)
+static bool env_switch_on(const char *name)
+{
+    const char *e = getenv(name);
+    return !(e && e[0] == '0');
+}
+static bool planar_enabled() { return env_switch_on("SCHW_PLANAR"); }
+static int32_t hi_word(double x)
+{
+    uint64_t u;
+    memcpy(&u, &x, 8);
+    return (int32_t)(u >> 32);
+}
+static double from_hi_word(int32_t hi)
+{
+    const uint64_t u = (uint64_t)(uint32_t)hi << 32;
+    double x;
+    memcpy(&x, &u, 8);
+    return x;
+}
+// Thresholds of the planar fast path (schw_device.cuh, "Planar steps"): pick r_thr below the capture radius, then
+// the largest |p_theta| bound T that makes (R1) and (R3) hold, then the |p_phi| bound that makes (R2) hold.
+static void make_planar_params(StepParams &P)
+{
+    const double cot_eq = 6.123233995736766e-17;   // cos/sin of the double nearest pi/2 (sin is exactly 1.0)
+    P.pl_hcA = P.delta * cot_eq;
+    P.pl_hcB = P.h * cot_eq;
+    P.pl_zero_hs = 0.0 * P.mhs;
+    P.pl_enable = 0; P.pl_ph_hi = 0; P.pl_r_hi = 0x7ff00000; P.pl_pp_hi = 0x7ff00000;
+    if (!planar_enabled()) return;
+    if (!(P.delta > 0.0) || !(P.delta < 1e6) || !(P.rcap > 0.0) || !(P.rcap < 1e300) || !(fabs(P.mhs) <= 0.5)) return;
+    const int32_t r_hi = hi_word(0.75 * P.rcap) + 1;               // hi(r) >= r_hi  =>  r >= r_thr > 0.75 rcap
+    const double r_thr = from_hi_word(r_hi);
+    double T = ldexp(1.0, -54) * r_thr * r_thr / P.delta;          // (R1), delta >= delta/2 covers both flows
+    if (P.mhs != 0.0) T = fmin(T, ldexp(1.0, -55) / fabs(P.mhs));  // (R3)
+    T = fmin(T, ldexp(1.0, -30));
+    if (!(T >= ldexp(1.0, -900))) return;
+    P.pl_ph_hi = hi_word(T);                                       // hi(|p|) < hi(T)  =>  |p| < T
+    P.pl_pp_hi = hi_word(ldexp(T, 28)) + 1;                        // hi(|p|) >= this  =>  |p| > 2^28 T
+    P.pl_r_hi = r_hi;
+    P.pl_enable = 1;
+}
+
 static int make_step_params(int64_t steps, double delta, double rs, double r_max, double omega, StepParams &P)
 {
     if (steps < 0 || steps > 0x7fffffffLL) return fail(SCHW_E_INVALID, "steps must be in [0, 2^31-1]");
@@ -668,6 +753,11 @@ static int make_step_params(int64_t steps, double delta, double rs, double r_max
     P.mhs = 0.5 * sin(ang);
     P.steps = (int32_t)steps;
     P._pad = 0;
+    // high-word pre-test of the termination test (maybe_finished): for 0 <= rcap and 0 < r_max the signed high words
+    // order like the doubles; otherwise (negative or NaN thresholds) the pre-test never rules termination out
+    P.hi_rcap = (P.rcap >= 0.0) ? hi_word(P.rcap) : 0x7fffffff;
+    P.hi_rmax = (P.r_max > 0.0) ? hi_word(P.r_max) : (int32_t)0x80000000;
+    make_planar_params(P);
     return SCHW_OK;
 }
 
@@ -737,31 +827,34 @@ static void end_timed(schw_handle *h, cudaStream_t st)
 }
 
 // SCHW_TRIG_MEMO=0 disables the exact sin/cos memoisation (A/B measurements; results are bit-identical).
-static bool trig_memo_enabled()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SCHW_TRIG_MEMO");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
+static bool trig_memo_enabled() { return env_switch_on("SCHW_TRIG_MEMO"); }
 
-template <class Job>
-static int launch_persistent(schw_handle *h, const Job &job, const StepParams &P, int occ, cudaStream_t st)
+template <class Job, bool kMemo, bool kPlanar>
+static int launch_variant(schw_handle *h, const Job &job, const StepParams &P, int &occ, cudaStream_t st)
 {
-    CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
-    if (job.n <= 0) return SCHW_OK;
-    long long want_blocks = (job.n + kBlock - 1) / kBlock;
+    auto kern = persistent_rays<Job, kMemo, kPlanar>;
+    if (occ == 0) {      // resident CTAs per SM of this variant (they differ in registers per thread)
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, 0));
+        if (occ < 1) return fail(SCHW_E_CUDA, "kernel does not fit on an SM");
+    }
+    const long long want_blocks = (job.n + kBlock - 1) / kBlock;
     long long grid = (long long)h->sm_count * occ;
     if (grid > want_blocks) grid = want_blocks;
-    if (trig_memo_enabled())
-        persistent_rays<Job, true><<<(unsigned)grid, kBlock, 0, st>>>(job, P, h->ctr);
-    else
-        persistent_rays<Job, false><<<(unsigned)grid, kBlock, 0, st>>>(job, P, h->ctr);
+    kern<<<(unsigned)grid, kBlock, 0, st>>>(job, P, h->ctr);
     h->launches += 1;
     CU(cudaGetLastError());
     return SCHW_OK;
+}
+
+// occ: the handle's three occupancy slots of this job type {no memo, memo, memo + planar}
+template <class Job>
+static int launch_persistent(schw_handle *h, const Job &job, const StepParams &P, int *occ, cudaStream_t st)
+{
+    CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
+    if (job.n <= 0) return SCHW_OK;
+    if (!trig_memo_enabled()) return launch_variant<Job, false, false>(h, job, P, occ[0], st);
+    if (!P.pl_enable) return launch_variant<Job, true, false>(h, job, P, occ[1], st);
+    return launch_variant<Job, true, true>(h, job, P, occ[2], st);
 }
 
 // ---- integrate_batch ----------------------------------------------------------------------------
@@ -1047,15 +1140,8 @@ static int build_tile_order(schw_handle *h, const schw_scene *s, const ScenePara
     return SCHW_OK;
 }
 
-static bool lpt_order_enabled()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SCHW_LPT_ORDER");      // SCHW_LPT_ORDER=0: plain row-major queue (A/B measurements)
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
+// SCHW_LPT_ORDER=0: plain row-major queue (A/B measurements)
+static bool lpt_order_enabled() { return env_switch_on("SCHW_LPT_ORDER"); }
 
 // ---- fused render -------------------------------------------------------------------------------
 extern "C" int schw_render_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex, int row_begin,

@@ -23,7 +23,7 @@ EXPORTS = (
     "schw_abi_version", "schw_last_error", "schw_create", "schw_destroy", "schw_device_info",
     "schw_last_kernel_ms", "schw_integrate_batch", "schw_integrate_batch_dev", "schw_integrate_batch_full", "schw_integrate_batch_rows",
     "schw_initial_conditions", "schw_initial_conditions_px", "schw_classify", "schw_render", "schw_render_dev", "schw_last_total_steps",
-    "schw_flat_render", "schw_fp64_peak_probe", "schw_math_probe",
+    "schw_flat_render", "schw_fp64_peak_probe", "schw_math_probe", "schw_last_counters",
 )
 
 
@@ -82,6 +82,7 @@ def load():
     L.schw_device_info.argtypes = [vp, C.c_char_p, i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.schw_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.schw_last_total_steps.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.schw_last_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.schw_integrate_batch.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp]
     L.schw_integrate_batch_dev.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp, vp]
     L.schw_integrate_batch_full.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp]
@@ -169,6 +170,12 @@ class Handle:
         v = C.c_uint64()
         _check(self._L.schw_last_total_steps(self._h, C.byref(v)))
         return int(v.value)
+
+    def last_counters(self):
+        """(total_steps, warp_iters, planar_iters) of the last render / integrate_batch call."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(self._L.schw_last_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
 
     def fp64_peak_probe(self):
         t, ms = C.c_double(), C.c_float()
