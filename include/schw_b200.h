@@ -20,6 +20,7 @@
 #ifndef SCHW_B200_H
 #define SCHW_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -86,6 +87,12 @@ int  schw_device_info(schw_handle *h, char *name, int name_cap, int *sm_count, i
 /* CUDA-event duration (ms) of the kernels enqueued by the last compute call on this handle,
  * measured on the stream they were launched on; and how many kernels that call launched. */
 int  schw_last_kernel_ms(schw_handle *h, float *ms, int *launches);
+
+/* Page-locked host memory for the caller's frame buffers (optional): host-pointer entry points copy at full PCIe rate
+ * into / out of such buffers, while ordinary pageable memory is staged by the driver at a fraction of it.  The reference
+ * has no counterpart (Numba's implicit transfers at cuda_geodesic.py:644,652 use pageable NumPy arrays). */
+int  schw_host_alloc(size_t bytes, void **out);
+int  schw_host_free(void *p);
 
 /* ---- stage 3+4: the integrator --------------------------------------------------------------
  * Replaces CUDASchwarzschildIntegrator.integrate_batch (simulation/cuda_geodesic.py:639-645,

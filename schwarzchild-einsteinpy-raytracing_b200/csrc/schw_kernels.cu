@@ -647,6 +647,26 @@ extern "C" int schw_destroy(schw_handle *h)
     return SCHW_OK;
 }
 
+extern "C" int schw_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(SCHW_E_INVALID, "schw_host_alloc: out is NULL");
+    *out = nullptr;
+    if (bytes == 0) return SCHW_OK;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        *out = nullptr;
+        return fail(SCHW_E_NOMEM, std::string("cudaHostAlloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    }
+    return SCHW_OK;
+}
+
+extern "C" int schw_host_free(void *p)
+{
+    if (!p) return SCHW_OK;
+    CU(cudaFreeHost(p));
+    return SCHW_OK;
+}
+
 extern "C" int schw_device_info(schw_handle *h, char *name, int name_cap, int *sm_count, int *clock_khz)
 {
     if (!h) return fail(SCHW_E_INVALID, "null handle");

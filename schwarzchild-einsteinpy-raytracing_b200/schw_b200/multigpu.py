@@ -117,9 +117,14 @@ def render_frame(scene, tex, extras=False, handle=None):
     dist.all_gather_into_tensor(B["gathered"], B["packed"])                            # THE collective of a frame
     # rank blocks -> natural row order on the device: row i = r + world*k lives at [r, k]
     nat = B["gathered"].view(world, max_rows, 4 * w).permute(1, 0, 2).reshape(world * max_rows, 4 * w)[:h]
-    rgb = np.empty((h, w, 3), np.uint8); cls = np.empty((h, w), np.uint8)               # fresh arrays, like the reference's np.zeros
-    torch.from_numpy(rgb).view(h, 3 * w).copy_(nat[:, :3 * w])                         # D2H straight into the results
-    torch.from_numpy(cls).copy_(nat[:, 3 * w:])
+    # fresh arrays like the reference's np.zeros, but page-locked (torch's caching host allocator recycles the blocks):
+    # the D2H of the frame then runs at PCIe rate instead of being staged through the driver's bounce buffers
+    rgb_t = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
+    cls_t = torch.empty((h, w), dtype=torch.uint8, pin_memory=True)
+    rgb_t.view(h, 3 * w).copy_(nat[:, :3 * w], non_blocking=True)                      # D2H straight into the results
+    cls_t.copy_(nat[:, 3 * w:], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    rgb, cls = rgb_t.numpy(), cls_t.numpy()
     res = dict(rgb=rgb, cls=cls, q0=q0[0])
     for k, t in ex.items():                                                            # diagnostics, on request only
         g = torch.empty((world * max_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)

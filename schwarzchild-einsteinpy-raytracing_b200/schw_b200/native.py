@@ -24,6 +24,7 @@ EXPORTS = (
     "schw_last_kernel_ms", "schw_integrate_batch", "schw_integrate_batch_dev", "schw_integrate_batch_full", "schw_integrate_batch_rows",
     "schw_initial_conditions", "schw_initial_conditions_px", "schw_classify", "schw_render", "schw_render_dev", "schw_last_total_steps",
     "schw_flat_render", "schw_fp64_peak_probe", "schw_math_probe", "schw_last_counters",
+    "schw_host_alloc", "schw_host_free",
 )
 
 
@@ -95,6 +96,8 @@ def load():
     L.schw_flat_render.argtypes = [vp, scp, vp, vp]
     L.schw_math_probe.argtypes = [vp, dp, i64, dp, dp, dp]
     L.schw_fp64_peak_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.schw_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.schw_host_free.argtypes = [vp]
     for name in EXPORTS:
         if name not in ("schw_last_error",):
             getattr(L, name).restype = C.c_int
@@ -118,6 +121,56 @@ def _check(rc):
 
 def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+# ---- page-locked frame buffers -----------------------------------------------------------------------
+# render() returns fresh arrays like the reference's np.zeros (raytracing.py:50), but backed by page-locked memory so
+# the D2H of a frame runs at PCIe rate (a 4K frame: 33 MB in ~0.6 ms instead of ~4 ms into pageable memory).  Blocks go
+# back to a small pool when the array is garbage-collected.
+_PINNED_POOL = {}          # nbytes -> [address, ...]
+_PINNED_POOL_MAX = 4       # blocks kept per size
+
+
+def _host_alloc(nbytes):
+    p = C.c_void_p()
+    _check(load().schw_host_alloc(nbytes, C.byref(p)))
+    return p.value
+
+
+def _host_free(addr):
+    load().schw_host_free(C.c_void_p(addr))
+
+
+class _PinnedBlock:
+    """Owner of one page-locked block: taken from the pool (or allocated) on creation, handed back on collection."""
+
+    def __init__(self, nbytes):
+        self.nbytes = nbytes
+        free = _PINNED_POOL.get(nbytes)
+        self.addr = free.pop() if free else _host_alloc(nbytes)
+
+    def __del__(self):
+        try:
+            free = _PINNED_POOL.setdefault(self.nbytes, [])
+            if len(free) < _PINNED_POOL_MAX:
+                free.append(self.addr)
+            else:
+                _host_free(self.addr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """Uninitialised page-locked ndarray (every element is overwritten by the D2H copy that follows).  A plain
+    np.ndarray: its buffer object keeps the block alive, so the block returns to the pool when the last view dies."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    if nbytes == 0:
+        return np.empty(shape, dtype)
+    blk = _PinnedBlock(nbytes)
+    buf = (C.c_uint8 * nbytes).from_address(blk.addr)
+    buf._owner = blk
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 def make_scene(obs=(30.0, 0.0, 0.0), fov=np.radians(80.0), height=400, width=400, mass=1.0, r_max=31.0,
@@ -266,7 +319,7 @@ class Handle:
         tex = None if tex is None else np.ascontiguousarray(tex, np.uint8)
         if tex is not None and tex.shape != (scene.height, scene.width, 3):
             raise ValueError("texture must be (height, width, 3) uint8 (the sky resized to the frame)")
-        rgb = np.zeros((nrows, w, 3), np.uint8); cls = np.zeros((nrows, w), np.uint8)
+        rgb = pinned_empty((nrows, w, 3), np.uint8); cls = pinned_empty((nrows, w), np.uint8)
         out = dict(rgb=rgb, cls=cls)
         x = None
         if extras:

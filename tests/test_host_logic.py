@@ -94,3 +94,33 @@ def test_run_manual_simulation_quirks_without_gpu(tmp_path, monkeypatch):
     assert img.shape == (6, 8, 3) and img.dtype == np.uint8 and not img.any()
     with pytest.raises(RuntimeError):
         run_manual_simulation(bh, ob, steps=10, delta=0.1, use_cuda=False, boundary_radius=31, n_samples=2)
+
+
+def test_pinned_frame_buffers_are_plain_arrays_and_recycled(monkeypatch):
+    """render() hands out page-locked frame buffers (schw_host_alloc) as plain ndarrays; a block returns to the pool
+    when the last view of it dies.  The allocator is replaced by malloc here (no GPU in this container)."""
+    import ctypes
+    import gc
+    from schw_b200 import native
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype = ctypes.c_void_p; libc.malloc.argtypes = [ctypes.c_size_t]; libc.free.argtypes = [ctypes.c_void_p]
+    allocs, frees = [], []
+    monkeypatch.setattr(native, "_host_alloc", lambda n: (allocs.append(n), libc.malloc(n))[1])
+    monkeypatch.setattr(native, "_host_free", lambda a: (frees.append(a), libc.free(a)))
+    monkeypatch.setattr(native, "_PINNED_POOL", {})
+    a = native.pinned_empty((4, 5, 3), np.uint8)
+    assert type(a) is np.ndarray and a.flags.writeable and a.flags.c_contiguous and a.shape == (4, 5, 3)
+    a[:] = 7
+    v = a[1:3]
+    del a; gc.collect()
+    assert native._PINNED_POOL.get(60, []) == [] and v.sum() == 7 * 30        # a view keeps the block alive
+    del v; gc.collect()
+    assert len(native._PINNED_POOL[60]) == 1
+    b = native.pinned_empty((60,), np.uint8)
+    assert allocs == [60] and native._PINNED_POOL[60] == []                    # recycled, not re-allocated
+    many = [native.pinned_empty((60,), np.uint8) for _ in range(7)]
+    del many, b; gc.collect()
+    assert len(native._PINNED_POOL[60]) == native._PINNED_POOL_MAX and len(frees) == 8 - native._PINNED_POOL_MAX
+    assert native.pinned_empty((0, 3), np.uint8).shape == (0, 3)
+    for addr in native._PINNED_POOL.pop(60):
+        libc.free(addr)
