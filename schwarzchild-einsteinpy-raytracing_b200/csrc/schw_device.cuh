@@ -24,20 +24,20 @@ namespace schw {
 // Parameters (passed by value as __grid_constant__ kernel arguments => constant bank operands)
 // ---------------------------------------------------------------------------------------------
 struct StepParams {
-    double h;        // 0.5*delta                         (cuda_geodesic.py:571-575)
-    double delta;    // full step, used for merged A(d)
-    double h_rs, d_rs; // h*rs, delta*rs
-    double rs;       // 2*mass                             (cuda_geodesic.py:635)
-    double rcap;     // 1.1*rs evaluated in FP64           (cuda_geodesic.py:598)
-    double r_max;
-    double mg, mhs;  // (1-cos(2 w d))/2, sin(2 w d)/2   (cuda_geodesic.py:545-546; cos/sin from host libm)
+    // (pairs that one flow reads together sit in one aligned 16-byte slot so that a single LDCU.128 can fetch them)
+    double h, h_rs;          // 0.5*delta, h*rs                   (cuda_geodesic.py:571-575)
+    double delta, d_rs;      // full step (merged A(d)), delta*rs
+    double mg, mhs;          // (1-cos(2 w d))/2, sin(2 w d)/2   (cuda_geodesic.py:545-546; cos/sin from host libm)
     // equatorial fast path (see "Planar steps" below); thresholds are compared on the high 32 bits of a double
-    double pl_hcA, pl_hcB;   // delta * cot(th_eq), (delta/2) * cot(th_eq), th_eq = the double nearest pi/2
+    double pl_hcB, pl_hcA;   // (delta/2) * cot(th_eq), delta * cot(th_eq), th_eq = the double nearest pi/2
+    double rs;               // 2*mass                             (cuda_geodesic.py:635)
     double pl_zero_hs;       // (+0) * mhs: the signed zero the mixed flow adds to p_theta when q1_theta == q2_theta
-    int32_t pl_enable;
+    double rcap;             // 1.1*rs evaluated in FP64           (cuda_geodesic.py:598)
+    double r_max;
     int32_t pl_ph_hi;        // |p_theta| <  T      <=  hi(|p_theta|) <  pl_ph_hi
     int32_t pl_r_hi;         // r         >= r_thr  <=  hi(r)         >= pl_r_hi   (signed compare)
     int32_t pl_pp_hi;        // |p_phi|   >  2^28 T <=  hi(|p_phi|)   >= pl_pp_hi
+    int32_t pl_enable;
     // termination pre-test on the high word of r (integer pipe): hi(r) > hi_rcap && hi(r) < hi_rmax  =>  rcap < r < r_max
     int32_t hi_rcap, hi_rmax;
     int32_t steps;
@@ -337,56 +337,62 @@ __device__ __forceinline__ void flow_C(RayState &S, double g, double hs)
 }
 
 // One full loop body B(d/2) C(d) B(d/2) A(d) with the planar fast path.
-//   tok    (warp-uniform, carried by the caller): (R0) and the tests of the first B held for every lane when the
-//          previous step ended; the caller clears it whenever lanes were given new rays.
+//   tok    (warp-uniform, carried by the caller, 0/1): (R0) and the tests of the first B hold for every lane, so
+//          the step may start on the fast path; the caller clears it whenever lanes were given new rays.
 //   pp_hi  this lane's |p_phi| threshold: P.pl_pp_hi while it integrates a ray, 0 while it is parked (parked lanes sit
 //          on the fixed point p = 0, theta = th_eq, where both variants of every flow are the identity and every other
 //          test passes by itself).
+//   next   (out, per lane) this lane passes the tests of the next step's first B; the caller votes on it together
+//          with its own end-of-step test and stores the result in tok.
+//   n_general (warp-uniform counter) incremented when the step did not run entirely on the fast path.
 // Each vote is issued as soon as its inputs exist and consumed only after the next flow_head, so its latency hides
-// behind independent FP64 work.  Returns whether the whole step ran on the fast path.  Must be called convergently.
-__device__ __forceinline__ bool step_BCBA_planar(RayState &S, const StepParams &P, Memo2 &M, int pp_hi, bool &tok)
+// behind independent FP64 work.  Must be called convergently.
+__device__ __forceinline__ void step_BCBA_planar(RayState &S, const StepParams &P, Memo2 &M, int pp_hi, int &tok,
+                                                 bool &next, int &n_general)
 {
     constexpr unsigned kFullMask = 0xffffffffu;
     const int T = P.pl_ph_hi, RT = P.pl_r_hi;
     if (!tok)       // after a refill, or while some lane carries a ray with polar motion
         tok = __all_sync(kFullMask, is_th_eq(S.q1h) & is_th_eq(S.q2h) &
                                     (hi_abs(S.p1h) < T) & (__double2hiint(S.q2r) >= RT) & (hi_abs(S.p1p) >= pp_hi));
+    // (general tails first: ptxas lays the first branch of an if/else out as the fall-through and the second one right
+    //  before the join, so the fast path costs one taken branch per flow instead of a not-taken plus a jump)
     // ---- B(d/2): reads (q2, p1), writes p2 and q1 ----
-    const bool v1 = tok;
+    const bool v1 = tok != 0;
     FlowHead f = flow_head(S.q2r, S.p1t, S.p1r, S.q1t, S.q1r, P.h, P.h_rs, P.rs);
-    if (__builtin_expect(v1, 1)) {
-        flow_tail_planar(f, S.p1p, P.pl_hcB, S.p2r, S.p2h, S.q1p, P.h);
-    } else {
+    if (!v1) {
         memo_refresh(S.q2h, P.h, M.m2);
         flow_tail(f, S.p1h, S.p1p, M.m2.is, M.m2.hcis, S.p2r, S.p2h, S.q1h, S.q1p, P.h);
+    } else {
+        flow_tail_planar(f, S.p1p, P.pl_hcB, S.p2r, S.p2h, S.q1p, P.h);
     }
     // ---- C(d), and the tests of the second B (its r and p_phi are final once their components are mixed) ----
     mix(S.q1r, S.p1r, S.q2r, S.p2r, P.mg, P.mhs);
     mix(S.q1p, S.p1p, S.q2p, S.p2p, P.mg, P.mhs);
     const bool v2 = __all_sync(kFullMask, v1 & (hi_abs(S.p2h) < T) & (__double2hiint(S.q2r) >= RT) & (hi_abs(S.p1p) >= pp_hi));
     mix(S.q1t, S.p1t, S.q2t, S.p2t, P.mg, P.mhs);
-    if (__builtin_expect(v2, 1)) mix_planar(S.p1h, S.p2h, P.mg, P.pl_zero_hs);
-    else mix(S.q1h, S.p1h, S.q2h, S.p2h, P.mg, P.mhs);
+    if (!v2) mix(S.q1h, S.p1h, S.q2h, S.p2h, P.mg, P.mhs);
+    else mix_planar(S.p1h, S.p2h, P.mg, P.pl_zero_hs);
     // ---- B(d/2) ----
     f = flow_head(S.q2r, S.p1t, S.p1r, S.q1t, S.q1r, P.h, P.h_rs, P.rs);
-    if (__builtin_expect(v2, 1)) {
-        flow_tail_planar(f, S.p1p, P.pl_hcB, S.p2r, S.p2h, S.q1p, P.h);
-    } else {
+    if (!v2) {
         memo_refresh(S.q2h, P.h, M.m2);
         flow_tail(f, S.p1h, S.p1p, M.m2.is, M.m2.hcis, S.p2r, S.p2h, S.q1h, S.q1p, P.h);
+    } else {
+        flow_tail_planar(f, S.p1p, P.pl_hcB, S.p2r, S.p2h, S.q1p, P.h);
     }
     // ---- A(d): reads (q1, p2), writes p1 and q2 ----
     const bool v4 = __all_sync(kFullMask, v2 & (hi_abs(S.p2h) < T) & (__double2hiint(S.q1r) >= RT) & (hi_abs(S.p2p) >= pp_hi));
     f = flow_head(S.q1r, S.p2t, S.p2r, S.q2t, S.q2r, P.delta, P.d_rs, P.rs);
-    if (__builtin_expect(v4, 1)) {
-        flow_tail_planar(f, S.p2p, P.pl_hcA, S.p1r, S.p1h, S.q2p, P.delta);
-    } else {
+    if (!v4) {
+        ++n_general;
         memo_refresh(S.q1h, P.delta, M.m1);
         flow_tail(f, S.p2h, S.p2p, M.m1.is, M.m1.hcis, S.p1r, S.p1h, S.q2h, S.q2p, P.delta);
+    } else {
+        flow_tail_planar(f, S.p2p, P.pl_hcA, S.p1r, S.p1h, S.q2p, P.delta);
     }
     // the next step's first B: its inputs (p1_th, q2_r, p1_ph) are final now
-    tok = __all_sync(kFullMask, v4 & (hi_abs(S.p1h) < T) & (__double2hiint(S.q2r) >= RT) & (hi_abs(S.p1p) >= pp_hi));
-    return v4;
+    next = v4 & (hi_abs(S.p1h) < T) & (__double2hiint(S.q2r) >= RT) & (hi_abs(S.p1p) >= pp_hi);
 }
 
 // B(d/2) C(d) B(d/2): the part of _fantasy_step_ord2 (cuda_geodesic.py:569-575) between the two

@@ -33,7 +33,7 @@ namespace schw {
 #define SCHW_BLOCK 128
 #endif
 #ifndef SCHW_MINBLOCKS
-#define SCHW_MINBLOCKS 6
+#define SCHW_MINBLOCKS 6   // 7 (72 registers, spills) measures the same, 5 is 1.7 % slower
 #endif
 #ifndef SCHW_MINBLOCKS_GENERAL
 #define SCHW_MINBLOCKS_GENERAL 5     // kernels without the planar fast path keep the trig memo in registers (94 of them)
@@ -197,8 +197,8 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     bool drained = false;        // queue is empty
     int it = 0;                  // warp-uniform iteration counter
     int debt = 0;                // lane-steps spent idle by waiting lanes since the last service (warp-uniform)
-    bool tok = false;            // planar fast path: the next step may start on it (warp-uniform, see step_BCBA_planar)
-    int npl = 0;                 // iterations completed on the planar fast path (warp-uniform)
+    int tok = 0;                 // planar fast path: the next step may start on it (warp-uniform, see step_BCBA_planar)
+    int n_general = 0;           // iterations that left the planar fast path (warp-uniform)
     int pp_hi = 0;               // planar fast path: this lane's |p_phi| threshold (0 while parked)
 
     // Lanes without a ray sit on a fixed point of all three flows (p = 0 => dq = dH = 0, mixing of
@@ -250,13 +250,14 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
         }
         if (__ballot_sync(kFull, active) == 0u) break;             // every lane is out of work
         debt = 0;
-        tok = false;                                               // new rays on board: re-establish (R0)
+        tok = 0;                                                   // new rays on board: re-establish (R0)
         pp_hi = active ? P.pl_pp_hi : 0;
 
         // ---- integrate; finished lanes park their result and idle until servicing them pays ----
         while (true) {
+            bool next = false;
             if (kPlanar) {
-                npl += step_BCBA_planar(S, P, M, pp_hi, tok);
+                step_BCBA_planar(S, P, M, pp_hi, tok, next, n_general);
             } else {
                 step_BCB<kMemo>(S, P, M);                           // q1 is now final for this step
                 flow_A<kMemo>(S, P.delta, P.d_rs, P.rs, M);         // trailing A(d/2) + next step's leading A(d/2)
@@ -266,7 +267,9 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
             // FP64 test only in the (rare) steps where some lane's pre-test cannot rule termination out
             const bool maybe = active & ((n >= P.steps) | maybe_finished(S.q1r, P));
             const bool tick = (it & 15) == 0;
-            if (__any_sync(kFull, maybe) || tick) {
+            // one vote per step on the fast path: "nobody may have finished and everybody may start the next step planar"
+            if (kPlanar) tok = __all_sync(kFull, next & !maybe);
+            if ((kPlanar && tok) ? tick : (__any_sync(kFull, maybe) || tick)) {
                 const bool done = maybe && (n >= P.steps || finished_or_nan(S.q1r, P));
                 const bool any_done = __any_sync(kFull, done);
                 // idle cost so far: every waiting lane wastes one lane-step per iteration (booked every 16 iterations)
@@ -291,7 +294,7 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     // ---- total step count (metric numerator) and loop statistics ----
     if (lane == 0 && it) {
         atomicAdd(&ctr->warp_iters, (unsigned long long)it);
-        if (npl) atomicAdd(&ctr->planar_iters, (unsigned long long)npl);
+        if (kPlanar) atomicAdd(&ctr->planar_iters, (unsigned long long)(it - n_general));
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_total) atomicAdd(&ctr->total_steps, s_total);
