@@ -221,7 +221,7 @@ def main():
     for _ in range(args.warmup):
         step_device()
     barrier()
-    steps_per_frame_local = hd.last_total_steps()
+    steps_per_frame_local, warp_iters, planar_iters = hd.last_counters()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -287,9 +287,14 @@ def main():
                          "executed_flop_per_step_ncu": ncu.get("executed_flop_per_step"),
                          "executed_tflops": (ncu["executed_flop_per_step"] * steps_per_frame_local / (kern_ms[-1] * 1e-3) / 1e12
                                              if "executed_flop_per_step" in ncu else None),
+                         "executed_fp64_instr_per_step_ncu": ncu.get("executed_fp64_warp_instructions_per_warp_step"),
+                         "lane_utilisation": steps_per_frame_local / (32.0 * warp_iters) if warp_iters else None,
+                         "planar_fast_path_fraction": planar_iters / warp_iters if warp_iters else None,
                          "note": "achieved counts the reference's ALGORITHMIC work (312 flop/step: 4 flow evaluations, 36 divisions, "
-                                 "8 sin/cos per step); the kernel executes ~173 flop/step (3 flow evaluations, 3 reciprocals, memoised "
-                                 "trig), so frac can exceed 1 -- pipe utilisation is fp64_pipe_pct_of_peak_ncu",
+                                 "8 sin/cos per step); the kernel executes far fewer (3 flow evaluations, 3 reciprocals, memoised trig, "
+                                 "theta sector skipped while it is provably a no-op: executed_flop_per_step_ncu), so frac can exceed 1 "
+                                 "-- pipe utilisation is fp64_pipe_pct_of_peak_ncu; lane_utilisation = ray-advancing share of the "
+                                 "lane-steps issued by the step loop (device counters of this run, rank 0)",
                          "algorithmic_bytes_per_launch": 7 * h * w,
                          "peak_source": "measured in this run (schw_fp64_peak_probe: register-resident DFMA chains); "
                                         f"nominal {NOMINAL_FP64_TFLOPS} TFLOP/s",

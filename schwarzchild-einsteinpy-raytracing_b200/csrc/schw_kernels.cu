@@ -49,6 +49,8 @@ struct Counters {
     unsigned long long total_steps;  // integrator steps executed
     unsigned long long warp_iters;   // loop bodies executed, summed over warps (32 x this = lane-steps issued)
     unsigned long long planar_iters; // of those, completed entirely on the planar fast path
+    int batch_planar;                // verdict of batch_probe_kernel
+    int _pad;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -60,7 +62,12 @@ struct BatchJob {
     double *__restrict__ out_qs;
     int32_t *__restrict__ out_steps;
     long long n;
+    // Kernel selection on the device: when `select` is set, this launch runs only if *select == want (see
+    // batch_probe_kernel / integrate_batch_impl); otherwise the whole grid exits at once.
+    const int *__restrict__ select;
+    int want;
 
+    __device__ __forceinline__ bool skip() const { return select && *select != want; }
     __device__ __forceinline__ long long queue_len() const { return n; }
     __device__ __forceinline__ long long resolve(long long q) const { return q; }
     // load(): initial (q0, p0) of ray k into this thread's shared-memory staging area st[0..3*kBlock]
@@ -73,6 +80,8 @@ struct BatchJob {
     }
     // cost of one divergent service pass (load + store) in lane-steps, for the batching rule of the kernel
     static constexpr int kServiceCost = 32;
+    // caller-supplied rays may have any polar motion: keep the trig memo in registers
+    static constexpr bool kMemoSmem = false;
     __device__ __forceinline__ void store(long long k, double t, double r, double th, double ph, int nsteps, bool nan_exit,
                                           const double2 &) const
     {
@@ -102,6 +111,7 @@ struct RenderJob {
     int32_t tiles_per_row;
     long long qlen;
 
+    __device__ __forceinline__ bool skip() const { return false; }
     __device__ __forceinline__ long long queue_len() const { return qlen; }
     __device__ __forceinline__ long long resolve(long long q) const
     {
@@ -131,6 +141,8 @@ struct RenderJob {
     // one service pass = classification epilogue + camera/initial-condition prologue, ~1500 instructions executed for
     // however few lanes need it = ~9 warp-steps = ~288 lane-steps
     static constexpr int kServiceCost = 288;
+    // the planar kernel is only launched for an observer in the equatorial plane (schw_render_dev): every ray is planar
+    static constexpr bool kMemoSmem = true;
     __device__ __forceinline__ void store(long long k, double t_, double r_, double th_, double ph_, int ns, bool nan_exit,
                                           const double2 &slot) const
     {
@@ -171,6 +183,7 @@ template <class Job, bool kMemo, bool kPlanar>
 __global__ void __launch_bounds__(kBlock, kPlanar ? SCHW_MINBLOCKS : SCHW_MINBLOCKS_GENERAL)
 persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepParams P, Counters *ctr)
 {
+    if (job.skip()) return;                   // (grid-uniform)
     __shared__ double2 s_slot[kBlock];        // (alpha0, beta) of the ray in flight, for its epilogue
     __shared__ double2 s_fin[4 * kBlock];     // staging: final (t,r),(theta,phi) of a finished ray awaiting service;
                                               // (q0, p0) of a fetched ray between load() and the state registers
@@ -181,14 +194,12 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     double2 &slot = s_slot[threadIdx.x];
     const unsigned lane = threadIdx.x & 31u;
     RayState S;
-#if SCHW_MEMO_SMEM
-    // On the planar fast path the trig memo is not touched, so it can live in shared memory (12 registers less).
-    __shared__ Memo2 s_memo[kPlanar ? kBlock : 1];
+    // On the planar fast path the trig memo is not touched, so for jobs known to live on it (Job::kMemoSmem) it sits in
+    // shared memory (12 registers less, which buys the 6th resident CTA).
+    constexpr bool kSmemMemo = SCHW_MEMO_SMEM && kPlanar && Job::kMemoSmem;
+    __shared__ Memo2 s_memo[kSmemMemo ? kBlock : 1];
     Memo2 M_reg;
-    Memo2 &M = kPlanar ? s_memo[threadIdx.x] : M_reg;
-#else
-    Memo2 M;
-#endif
+    Memo2 &M = kSmemMemo ? s_memo[threadIdx.x] : M_reg;
     M.init(P.delta, P.h);        // m1 serves the merged A(delta) of the step loop, m2 the two B(delta/2)
     int k = -1;                  // ray in flight, or finished ray awaiting service (n < 2^31 is checked on the host)
     int n = 0;                   // steps taken by the ray in flight
@@ -396,6 +407,30 @@ integrate_rows_kernel(const double *__restrict__ q0s, const double *__restrict__
     }
     if (out_rows) out_rows[i] = rows;
     atomicAdd(&ctr->total_steps, (unsigned long long)(rows > 0 ? rows - 1 : 0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Is a batch of caller-supplied rays worth the kernel with the planar fast path?  Only if (nearly) all of them start
+// in the equatorial plane without polar momentum, like the reference's camera rays (utils.py:129,172): a warp leaves
+// the fast path as soon as one of its lanes carries a tilted ray, and the fast-path kernel is slower than the plain one
+// on such warps.  One CTA looks at up to 4096 evenly spaced rays and leaves the verdict in *flag; both kernels are then
+// enqueued and the one that was not chosen exits immediately (BatchJob::skip) -- no host round trip.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+batch_probe_kernel(const double *__restrict__ q0s, const double *__restrict__ p0s, long long n, int *__restrict__ flag)
+{
+    __shared__ int hits;
+    if (threadIdx.x == 0) hits = 0;
+    __syncthreads();
+    const long long m = n < 4096 ? n : 4096;
+    int mine = 0;
+    for (long long k = threadIdx.x; k < m; k += blockDim.x) {
+        const long long i = (k * n) / m;
+        mine += is_th_eq(q0s[4 * i + 2]) && fabs(p0s[4 * i + 2]) < 1e-18;
+    }
+    if (mine) atomicAdd(&hits, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = (long long)hits * 10 >= m * 9;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -725,6 +760,13 @@ static bool env_switch_on(const char *name)
     return !(e && e[0] == '0');
 }
 static bool planar_enabled() { return env_switch_on("SCHW_PLANAR"); }
+// SCHW_PLANAR=2: use the fast-path kernel for every integrate_batch call, whatever the rays look like (tests of the
+// per-warp switching between the two paths on mixed batches; by default the device picks, see batch_probe_kernel)
+static bool planar_forced()
+{
+    const char *e = getenv("SCHW_PLANAR");
+    return e && e[0] == '2';
+}
 static int32_t hi_word(double x)
 {
     uint64_t u;
@@ -871,9 +913,10 @@ static int launch_variant(schw_handle *h, const Job &job, const StepParams &P, i
 
 // occ: the handle's three occupancy slots of this job type {no memo, memo, memo + planar}
 template <class Job>
-static int launch_persistent(schw_handle *h, const Job &job, const StepParams &P, int *occ, cudaStream_t st)
+static int launch_persistent(schw_handle *h, const Job &job, const StepParams &P, int *occ, cudaStream_t st,
+                             bool reset_counters = true)
 {
-    CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
+    if (reset_counters) CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
     if (job.n <= 0) return SCHW_OK;
     if (!trig_memo_enabled()) return launch_variant<Job, false, false>(h, job, P, occ[0], st);
     if (!P.pl_enable) return launch_variant<Job, true, false>(h, job, P, occ[1], st);
@@ -881,9 +924,9 @@ static int launch_persistent(schw_handle *h, const Job &job, const StepParams &P
 }
 
 // ---- integrate_batch ----------------------------------------------------------------------------
-extern "C" int schw_integrate_batch_dev(schw_handle *h, const double *d_q0s, const double *d_p0s, int64_t n,
-                                        int64_t steps, double delta, double rs, double r_max, double omega,
-                                        double *d_out_qs, int32_t *d_out_steps, void *cuda_stream)
+static int integrate_batch_impl(schw_handle *h, const double *d_q0s, const double *d_p0s, int64_t n,
+                                int64_t steps, double delta, double rs, double r_max, double omega,
+                                double *d_out_qs, int32_t *d_out_steps, void *cuda_stream)
 {
     if (!h) return fail(SCHW_E_INVALID, "null handle");
     if (n < 0 || n > 0x7fffffffLL) return fail(SCHW_E_INVALID, "n must be in [0, 2^31-1]");
@@ -893,11 +936,33 @@ extern "C" int schw_integrate_batch_dev(schw_handle *h, const double *d_q0s, con
     int rc = make_step_params(steps, delta, rs, r_max, omega, P);
     if (rc) return rc;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
-    BatchJob job{d_q0s, d_p0s, d_out_qs, d_out_steps, (long long)n};
+    BatchJob job{d_q0s, d_p0s, d_out_qs, d_out_steps, (long long)n, nullptr, 0};
     begin_timed(h, st);
-    rc = launch_persistent(h, job, P, h->occ_batch, st);
+    if (n > 0 && P.pl_enable && trig_memo_enabled() && !planar_forced()) {
+        // let the device choose between the kernel with the planar fast path and the plain one (batch_probe_kernel)
+        CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
+        batch_probe_kernel<<<1, 256, 0, st>>>(d_q0s, d_p0s, (long long)n, &h->ctr->batch_planar);
+        h->launches += 1;
+        CU(cudaGetLastError());
+        job.select = &h->ctr->batch_planar;
+        job.want = 1;
+        rc = launch_persistent(h, job, P, h->occ_batch, st, false);
+        if (rc) return rc;
+        job.want = 0;
+        P.pl_enable = 0;
+        rc = launch_persistent(h, job, P, h->occ_batch, st, false);
+    } else {
+        rc = launch_persistent(h, job, P, h->occ_batch, st);
+    }
     end_timed(h, st);
     return rc;
+}
+
+extern "C" int schw_integrate_batch_dev(schw_handle *h, const double *d_q0s, const double *d_p0s, int64_t n,
+                                        int64_t steps, double delta, double rs, double r_max, double omega,
+                                        double *d_out_qs, int32_t *d_out_steps, void *cuda_stream)
+{
+    return integrate_batch_impl(h, d_q0s, d_p0s, n, steps, delta, rs, r_max, omega, d_out_qs, d_out_steps, cuda_stream);
 }
 
 extern "C" int schw_integrate_batch(schw_handle *h, const double *q0s, const double *p0s, int64_t n,
@@ -915,8 +980,8 @@ extern "C" int schw_integrate_batch(schw_handle *h, const double *q0s, const dou
         CU(cudaMemcpyAsync(h->in_a.p, q0s, b, cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(h->in_b.p, p0s, b, cudaMemcpyHostToDevice, h->stream));
     }
-    int rc = schw_integrate_batch_dev(h, (const double *)h->in_a.p, (const double *)h->in_b.p, n, steps, delta, rs, r_max,
-                                      omega, (double *)h->fq.p, out_steps ? (int32_t *)h->nsteps.p : nullptr, nullptr);
+    int rc = integrate_batch_impl(h, (const double *)h->in_a.p, (const double *)h->in_b.p, n, steps, delta, rs, r_max,
+                                  omega, (double *)h->fq.p, out_steps ? (int32_t *)h->nsteps.p : nullptr, nullptr);
     if (rc) return rc;
     if (n > 0) {
         CU(cudaMemcpyAsync(out_qs, h->fq.p, b, cudaMemcpyDeviceToHost, h->stream));
@@ -1182,6 +1247,9 @@ extern "C" int schw_render_dev(schw_handle *h, const schw_scene *scene, const ui
     if (scene->has_texture && !d_tex) return fail(SCHW_E_INVALID, "has_texture set but tex is NULL");
     const long long n = (long long)sc.nrows * sc.width;
     if (n > 0 && (!d_rgb || !d_cls)) return fail(SCHW_E_INVALID, "null output");
+    // Camera rays start at theta_obs with p_theta = -0.0: they are eligible for the planar fast path iff theta_obs is
+    // the double nearest pi/2 (observer in the equatorial plane, the reference's only camera: raytracing.py:60-72).
+    if (sc.th_obs != 1.5707963267948966) P.pl_enable = 0;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     RenderJob job;
     job.sc = sc; job.tex = d_tex; job.rgb = d_rgb; job.cls = d_cls;

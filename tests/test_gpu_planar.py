@@ -54,32 +54,43 @@ def test_render_is_bit_identical_with_and_without_the_fast_path(handle, monkeypa
 
 
 def test_integrate_batch_is_bit_identical_with_and_without_the_fast_path(handle, monkeypatch):
-    # half camera-like equatorial rays, half tilted rays, in one queue: warps switch between the two paths
-    q0s, p0s = random_rays(6000, seed=21)
+    # camera-like equatorial rays first, then tilted rays, in one queue: warps start on the fast path, meet the odd rays
+    # below and the tilted ones as their lanes refill, and switch paths lane group by lane group
+    qa, pa = random_rays(6000, seed=21)
+    eq = qa[:, 2] == np.pi / 2
+    order = np.concatenate([np.flatnonzero(eq), np.flatnonzero(~eq)])
+    q0s, p0s = qa[order].copy(), pa[order].copy()
     # some rays that sit on theta == th_eq but violate the other conditions of the fast path
-    q0s[:64, 2] = np.pi / 2
-    p0s[:16, 2] = 1e-13                 # |p_theta| above the bound T
-    p0s[16:32, 3] = 1e-9                # |p_phi| below 2^28 T
-    p0s[32:48, 2] = -0.0
-    p0s[48:56, 3] = 0.0                 # exactly radial
-    q0s[56:60, 1] = np.nan
-    p0s[60:64, 2] = np.nan
+    m = 1500
+    q0s[m:m + 64, 2] = np.pi / 2
+    p0s[m:m + 16, 2] = 1e-13            # |p_theta| above the bound T
+    p0s[m + 16:m + 32, 3] = 1e-9        # |p_phi| below 2^28 T
+    p0s[m + 32:m + 48, 2] = -0.0
+    p0s[m + 48:m + 56, 3] = 0.0         # exactly radial
+    q0s[m + 56:m + 60, 1] = np.nan
+    p0s[m + 60:m + 64, 2] = np.nan
     res = {}
     for planar in (True, False):
-        monkeypatch.setenv("SCHW_PLANAR", "1" if planar else "0")
+        # "2": the fast-path kernel even though the host-side sample of this batch is not (nearly) all planar
+        monkeypatch.setenv("SCHW_PLANAR", "2" if planar else "0")
         out, ns = handle.integrate_batch(q0s, p0s, 3000, 0.02, 2.0, 45.0, 1.0, want_steps=True)
         res[planar] = (out, ns, handle.last_counters())
     assert np.array_equal(_bits(res[True][0]), _bits(res[False][0]))
     assert np.array_equal(res[True][1], res[False][1])
     assert res[False][2][2] == 0 and res[True][2][0] == res[False][2][0]
+    assert 0 < res[True][2][2] < res[True][2][1]          # some warps on the fast path, some off it
+    # default: the host looks at the batch and picks the plain kernel for it
+    monkeypatch.setenv("SCHW_PLANAR", "1")
+    out = handle.integrate_batch(q0s, p0s, 3000, 0.02, 2.0, 45.0, 1.0)
+    assert handle.last_counters()[2] == 0 and np.array_equal(_bits(out), _bits(res[False][0]))
     # all-equatorial batch: fast path taken; all-tilted batch: never
     qe, pe = random_rays(2048, seed=5, equatorial_frac=1.0)
-    monkeypatch.setenv("SCHW_PLANAR", "1")
     handle.integrate_batch(qe, pe, 12000, 0.005, 2.0, 45.0, 1.0)
     _, iters, planar_iters = handle.last_counters()
     # (rays with a large angular momentum L collect p_theta = cot(th_eq) L dphi beyond the bound T and leave the path)
     assert planar_iters > 0.5 * iters, (planar_iters, iters)
     qt, pt = random_rays(2048, seed=6, equatorial_frac=0.0)
+    monkeypatch.setenv("SCHW_PLANAR", "2")
     handle.integrate_batch(qt, pt, 3000, 0.02, 2.0, 45.0, 1.0)
     assert handle.last_counters()[2] == 0
 
