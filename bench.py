@@ -151,7 +151,8 @@ def workload_config(args, n):
     return {"workload": f"{args.width}x{args.height} Schwarzschild lensing frame, default config.py scene "
                         f"(obs (30,0,0), fov 80deg, r_max 31, delta 0.01, steps cap 200000, omega_eff 1.0, full-sky patch), "
                         f"synthetic sky texture", "height": args.height, "width": args.width,
-            "sharding": f"row-cyclic over {n} rank(s), one all_gather of rgb+class per frame" if n > 1 else "single GPU",
+            "sharding": (f"row-cyclic over {n} rank(s); value: one all_gather of rgb+class per frame; e2e: every rank uploads "
+                         f"the texture, one gather of rgb+class to rank 0, one D2H there") if n > 1 else "single GPU",
             "l2": "L2 flushed (256 MiB memset) between timed frames"}
 
 
@@ -244,7 +245,8 @@ def main():
     # ---- e2e: the host-buffer C-ABI call a user makes (texture H2D + outputs D2H inside the timed region) ----
     def step_e2e():
         # the call a user of the package makes: host texture in, host frame out (sharded + gathered when world > 1)
-        return render_frame(scene, tex_host.numpy(), handle=hd)["rgb"]
+        # (world > 1: root=0 = the single NCCL gather of rgb + class to rank 0, which copies the frame to the host once)
+        return render_frame(scene, tex_host.numpy(), handle=hd, root=0)["rgb"]
     step_e2e()
     barrier()
     t0 = time.perf_counter()

@@ -155,6 +155,11 @@ int  schw_render_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_t
                      int row_begin, int row_end, int row_stride,
                      uint8_t *d_rgb, uint8_t *d_cls, const schw_ray_outputs *d_extra,
                      void *cuda_stream);
+/* Overlap of the texture upload with the start of a frame (optional, one-shot): the next schw_render_dev call on this
+ * handle may be enqueued BEFORE its texture has arrived in d_tex; the kernel waits -- per ray, only at the texel lookup
+ * that ends it -- until the 32-bit word at d_flag is non-zero.  The caller clears the word, uploads the texture on
+ * another stream and sets the word with a copy ordered after that upload.  schw_render does this internally. */
+int  schw_set_tex_ready_flag(schw_handle *h, const uint32_t *d_flag);
 /* Sum of integrator steps over the rays of the last schw_render* / schw_integrate_batch* call on
  * this handle (device-side counter; used for the steps/s metric). */
 int  schw_last_total_steps(schw_handle *h, uint64_t *total_steps);

@@ -23,7 +23,7 @@ namespace schw {
 // ---------------------------------------------------------------------------------------------
 // Parameters (passed by value as __grid_constant__ kernel arguments => constant bank operands)
 // ---------------------------------------------------------------------------------------------
-struct StepParams {
+struct alignas(16) StepParams {
     // (pairs that one flow reads together sit in one aligned 16-byte slot so that a single LDCU.128 can fetch them)
     double h, h_rs;          // 0.5*delta, h*rs                   (cuda_geodesic.py:571-575)
     double delta, d_rs;      // full step (merged A(d)), delta*rs

@@ -68,6 +68,8 @@ struct BatchJob {
     int want;
 
     __device__ __forceinline__ bool skip() const { return select && *select != want; }
+    __device__ __forceinline__ const unsigned *ready_flag() const { return nullptr; }
+    __device__ __forceinline__ bool ends_at_once(const StepParams &) const { return false; }
     __device__ __forceinline__ long long queue_len() const { return n; }
     __device__ __forceinline__ long long resolve(long long q) const { return q; }
     // load(): initial (q0, p0) of ray k into this thread's shared-memory staging area st[0..3*kBlock]
@@ -93,9 +95,21 @@ struct BatchJob {
     }
 };
 
+// Warp-uniform bounded spin (about 2 s, then give up and read whatever is there) until the word at `flag` is non-zero.
+// The flag is written by a copy-engine memcpy that is stream-ordered after the texture upload, so a frame's integration
+// starts while its texture is still crossing PCIe; the first rays end milliseconds later, normally long after the flag.
+// The exit test is a vote, so the loop is convergent by construction (call from convergent code only).
+__device__ __forceinline__ void wait_flag_warp(const unsigned *flag)
+{
+    const volatile unsigned *f = flag;
+    for (int spin = 0; spin < (1 << 22) && !__any_sync(0xffffffffu, *f != 0u); ++spin) __nanosleep(512);
+    __threadfence();
+}
+
 struct RenderJob {
     SceneParams sc;
     const uint8_t *__restrict__ tex;
+    const unsigned *tex_ready;          // NULL, or the flag that says the texture upload has landed (see wait_flag)
     uint8_t *__restrict__ rgb;
     uint8_t *__restrict__ cls;
     double *__restrict__ final_q;
@@ -112,6 +126,10 @@ struct RenderJob {
     long long qlen;
 
     __device__ __forceinline__ bool skip() const { return false; }
+    // the flag a warp must see before its first epilogue (texel lookup), or NULL
+    __device__ __forceinline__ const unsigned *ready_flag() const { return tex_ready; }
+    // every ray of the frame starts at r_obs: do the rays end before their first step (cuda_geodesic.py:598)?
+    __device__ __forceinline__ bool ends_at_once(const StepParams &P) const { return P.steps <= 0 || terminated(sc.r_obs, P); }
     __device__ __forceinline__ long long queue_len() const { return qlen; }
     __device__ __forceinline__ long long resolve(long long q) const
     {
@@ -217,8 +235,13 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     // inf/NaN operands (which would send the trig/reciprocal code down slow paths for the whole warp).
     park(S, P);
 
+    bool inputs_ready = job.ready_flag() == nullptr;     // (warp-uniform) the texture upload of this frame has landed
     while (true) {
         // ---- service (divergent, so batched): epilogue of the finished rays, then refill ----
+        if (!inputs_ready && (job.ends_at_once(P) || __any_sync(kFull, waiting))) {
+            wait_flag_warp(job.ready_flag());                      // the first epilogue of this warp: its texel lookup
+            inputs_ready = true;
+        }
         if (waiting) {
             const double2 a = s_fin[threadIdx.x], b = s_fin[kBlock + threadIdx.x];
             job.store(k, a.x, a.y, b.x, b.y, s_nsteps[threadIdx.x], !(a.y == a.y), slot);
@@ -608,6 +631,11 @@ struct schw_handle {
     char name[256] = {0};
     cudaStream_t stream = nullptr;
     cudaStream_t last_stream = nullptr;   // stream of the last timed call (for result read-back ordering)
+    cudaStream_t copy_stream = nullptr;   // texture uploads of schw_render, overlapped with the start of the kernel
+    cudaEvent_t ev_copy0 = nullptr, ev_copy1 = nullptr;
+    unsigned *tex_flag = nullptr;         // device word: "texture of the current frame has landed"
+    unsigned *one_pinned = nullptr;       // page-locked 1, the source of the copy that raises tex_flag
+    const unsigned *next_tex_ready = nullptr;   // one-shot flag for the next schw_render_dev (schw_set_tex_ready_flag)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int launches = 0;
@@ -662,6 +690,12 @@ extern "C" int schw_create(int device, schw_handle **out)
     CU(cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, device));
     snprintf(h->name, sizeof(h->name), "%s", prop.name);
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_copy0, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_copy1, cudaEventDisableTiming));
+    CU(cudaMalloc(&h->tex_flag, sizeof(unsigned)));
+    CU(cudaHostAlloc(&h->one_pinned, sizeof(unsigned), cudaHostAllocDefault));
+    *h->one_pinned = 1u;
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     CU(cudaMalloc(&h->ctr, sizeof(Counters)));
@@ -678,6 +712,11 @@ extern "C" int schw_destroy(schw_handle *h)
     DevBuf *bufs[] = {&h->in_a, &h->in_b, &h->in_c, &h->tex, &h->rgb, &h->cls, &h->fq, &h->ic, &h->hit, &h->texel, &h->nsteps, &h->traj, &h->rows, &h->order};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (h->ctr) cudaFree(h->ctr);
+    if (h->tex_flag) cudaFree(h->tex_flag);
+    if (h->one_pinned) cudaFreeHost(h->one_pinned);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_copy0) cudaEventDestroy(h->ev_copy0);
+    if (h->ev_copy1) cudaEventDestroy(h->ev_copy1);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -1253,6 +1292,8 @@ extern "C" int schw_render_dev(schw_handle *h, const schw_scene *scene, const ui
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     RenderJob job;
     job.sc = sc; job.tex = d_tex; job.rgb = d_rgb; job.cls = d_cls;
+    job.tex_ready = scene->has_texture ? h->next_tex_ready : nullptr;
+    h->next_tex_ready = nullptr;
     job.final_q = x ? x->final_q : nullptr;
     job.ic = x ? x->ic : nullptr;
     job.hit = x ? x->hit : nullptr;
@@ -1272,6 +1313,13 @@ extern "C" int schw_render_dev(schw_handle *h, const schw_scene *scene, const ui
     return rc;
 }
 
+extern "C" int schw_set_tex_ready_flag(schw_handle *h, const uint32_t *d_flag)
+{
+    if (!h) return fail(SCHW_E_INVALID, "null handle");
+    h->next_tex_ready = reinterpret_cast<const unsigned *>(d_flag);
+    return SCHW_OK;
+}
+
 extern "C" int schw_render(schw_handle *h, const schw_scene *scene, const uint8_t *tex, int row_begin, int row_end,
                            int row_stride, uint8_t *rgb, uint8_t *cls, const schw_ray_outputs *x)
 {
@@ -1286,7 +1334,18 @@ extern "C" int schw_render(schw_handle *h, const schw_scene *scene, const uint8_
     if (n > 0 && (!rgb || !cls)) return fail(SCHW_E_INVALID, "null output");
     cudaStream_t st = h->stream;
     const size_t tb = (size_t)scene->height * scene->width * 3;
-    if (scene->has_texture) { ENSURE(h->tex, tb); CU(cudaMemcpyAsync(h->tex.p, tex, tb, cudaMemcpyHostToDevice, st)); }
+    if (scene->has_texture) {
+        // Upload on the copy stream and raise tex_flag behind it; the kernel is launched at once on `st` and only the
+        // epilogue of a ray (its texel lookup) waits for the flag.
+        ENSURE(h->tex, tb);
+        CU(cudaMemsetAsync(h->tex_flag, 0, sizeof(unsigned), st));
+        CU(cudaEventRecord(h->ev_copy0, st));                   // (also orders this upload after the previous frame's kernel)
+        CU(cudaStreamWaitEvent(h->copy_stream, h->ev_copy0, 0));
+        CU(cudaMemcpyAsync(h->tex.p, tex, tb, cudaMemcpyHostToDevice, h->copy_stream));
+        CU(cudaMemcpyAsync(h->tex_flag, h->one_pinned, sizeof(unsigned), cudaMemcpyHostToDevice, h->copy_stream));
+        CU(cudaEventRecord(h->ev_copy1, h->copy_stream));
+        h->next_tex_ready = h->tex_flag;
+    }
     ENSURE(h->rgb, n * 3 + 1); ENSURE(h->cls, n + 1);
     schw_ray_outputs d = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (x) {
@@ -1298,6 +1357,8 @@ extern "C" int schw_render(schw_handle *h, const schw_scene *scene, const uint8_
     }
     int rc = schw_render_dev(h, scene, scene->has_texture ? (const uint8_t *)h->tex.p : nullptr, row_begin, row_end,
                              row_stride, (uint8_t *)h->rgb.p, (uint8_t *)h->cls.p, &d, nullptr);
+    h->next_tex_ready = nullptr;
+    if (scene->has_texture) CU(cudaStreamWaitEvent(st, h->ev_copy1, 0));   // the upload is part of this call
     if (rc) return rc;
     if (n > 0) {
         CU(cudaMemcpyAsync(rgb, h->rgb.p, n * 3, cudaMemcpyDeviceToHost, st));

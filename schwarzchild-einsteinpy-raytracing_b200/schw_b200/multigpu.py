@@ -77,12 +77,14 @@ def _torch_stream_ptr():
     return p if p else 1
 
 
-def render_frame(scene, tex, extras=False, handle=None):
+def render_frame(scene, tex, extras=False, handle=None, root=None):
     """Render the whole frame of `scene`; sharded + gathered when torch.distributed is initialised.
 
-    world == 1: the host-buffer C-ABI call.  world > 1: the texture is uploaded once per rank, the rank's rows
-    are rendered into device buffers (schw_render_dev on torch's current stream), the packed (rows, 4w) u8
-    blocks are all_gather'ed on the device (NCCL) and copied to the host once.
+    world == 1: the host-buffer C-ABI call.  world > 1: every rank uploads the texture on a side stream while its rows
+    are already being integrated (schw_render_dev on torch's current stream; the kernel waits for the upload only at its
+    first texel lookup), the packed (rows, 4w) u8 blocks are exchanged on the device with ONE NCCL collective and copied
+    to page-locked host arrays.  root=None: all_gather, every rank returns the frame; root=r: gather, only rank r
+    receives and returns it (the other ranks get rgb = cls = None) -- the frame then crosses PCIe once, not once per rank.
 
     Returns dict(rgb (h,w,3) u8, cls (h,w) u8, q0 (4,)) plus, with extras, final_q (n,4), ic (n,9),
     hit (n,2), uv (n,2), nsteps (n,) in natural pixel order."""
@@ -105,33 +107,57 @@ def render_frame(scene, tex, extras=False, handle=None):
     dev = torch.device("cuda", torch.cuda.current_device())
     max_rows = (h + world - 1) // world
     B = _buffers(dev, h, w, world, extras, tex is not None)
+    main = torch.cuda.current_stream()
+    d_flag = 0
     if tex is not None:
-        B["tex"].copy_(torch.from_numpy(np.ascontiguousarray(tex, np.uint8)), non_blocking=True)
+        # texture upload on the side stream, flag raised behind it (schw_set_tex_ready_flag)
+        B["flag"].zero_()
+        B["side"].wait_stream(main)
+        with torch.cuda.stream(B["side"]):
+            B["tex"].copy_(torch.from_numpy(np.ascontiguousarray(tex, np.uint8)), non_blocking=True)
+            B["flag"].copy_(B["one"], non_blocking=True)
+        d_flag = B["flag"].data_ptr()
     ex = B["extras"]
     hd.render_dev(scene, B["tex"].data_ptr() if tex is not None else 0, rb, re, rs,
                   B["rgb"].data_ptr(), B["cls"].data_ptr(), stream=_torch_stream_ptr(),
                   d_final_q=ex["final_q"].data_ptr() if extras else 0, d_ic=ex["ic"].data_ptr() if extras else 0,
                   d_hit=ex["hit"].data_ptr() if extras else 0, d_texel=ex["uv"].data_ptr() if extras else 0,
-                  d_nsteps=ex["nsteps"].data_ptr() if extras else 0)
+                  d_nsteps=ex["nsteps"].data_ptr() if extras else 0, d_tex_ready=d_flag)
+    if tex is not None:
+        main.wait_stream(B["side"])                 # the upload belongs to this frame (and B["tex"] is reused by the next)
     torch.cat([B["rgb"].view(max_rows, 3 * w), B["cls"]], dim=1, out=B["packed"])     # (max_rows, 4w) u8
-    dist.all_gather_into_tensor(B["gathered"], B["packed"])                            # THE collective of a frame
-    # rank blocks -> natural row order on the device: row i = r + world*k lives at [r, k]
-    nat = B["gathered"].view(world, max_rows, 4 * w).permute(1, 0, 2).reshape(world * max_rows, 4 * w)[:h]
-    # fresh arrays like the reference's np.zeros, but page-locked (torch's caching host allocator recycles the blocks):
-    # the D2H of the frame then runs at PCIe rate instead of being staged through the driver's bounce buffers
-    rgb_t = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
-    cls_t = torch.empty((h, w), dtype=torch.uint8, pin_memory=True)
-    rgb_t.view(h, 3 * w).copy_(nat[:, :3 * w], non_blocking=True)                      # D2H straight into the results
-    cls_t.copy_(nat[:, 3 * w:], non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    rgb, cls = rgb_t.numpy(), cls_t.numpy()
-    res = dict(rgb=rgb, cls=cls, q0=q0[0])
+    mine = root is None or rank == root
+
+    def exchange(full, part):                       # THE collective of a frame (one more per diagnostic array)
+        if root is None:
+            dist.all_gather_into_tensor(full, part)
+        else:
+            dist.gather(part, list(full.view((world,) + tuple(part.shape)).unbind(0)) if mine else None, dst=root)
+
+    exchange(B["gathered"], B["packed"])
+    res = dict(rgb=None, cls=None, q0=q0[0])
+    if mine:
+        # rank blocks -> natural row order on the device: row i = r + world*k lives at [r, k]
+        nat = B["gathered"].view(world, max_rows, 4 * w).permute(1, 0, 2).reshape(world * max_rows, 4 * w)[:h]
+        # fresh arrays like the reference's np.zeros, but page-locked (torch's caching host allocator recycles the
+        # blocks): the D2H of the frame runs at PCIe rate instead of being staged through the driver's bounce buffers
+        rgb_t = torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True)
+        cls_t = torch.empty((h, w), dtype=torch.uint8, pin_memory=True)
+        rgb_t.view(h, 3 * w).copy_(nat[:, :3 * w], non_blocking=True)                  # D2H straight into the results
+        cls_t.copy_(nat[:, 3 * w:], non_blocking=True)
+        main.synchronize()
+        res.update(rgb=rgb_t.numpy(), cls=cls_t.numpy())
     for k, t in ex.items():                                                            # diagnostics, on request only
-        g = torch.empty((world * max_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        dist.all_gather_into_tensor(g, t)
+        g = torch.empty((world * max_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) if mine else None
+        exchange(g, t)
+        if not mine:
+            res[k] = None
+            continue
         g = g.view((world, max_rows) + tuple(t.shape[1:])).transpose(0, 1).reshape((world * max_rows,) + tuple(t.shape[1:]))[:h]
         a = g.cpu().numpy()
         res[k] = a.reshape(h * w, -1) if a.ndim == 3 else a.reshape(h * w)
+    if not mine:
+        main.synchronize()
     return res
 
 
@@ -149,7 +175,9 @@ def _buffers(dev, h, w, world, extras, has_tex):
                  rgb=torch.zeros((max_rows, w, 3), dtype=torch.uint8, device=dev),
                  cls=torch.zeros((max_rows, w), dtype=torch.uint8, device=dev),
                  packed=torch.empty((max_rows, 4 * w), dtype=torch.uint8, device=dev),
-                 gathered=torch.empty((world * max_rows, 4 * w), dtype=torch.uint8, device=dev), extras={})
+                 gathered=torch.empty((world * max_rows, 4 * w), dtype=torch.uint8, device=dev), extras={},
+                 side=torch.cuda.Stream(device=dev), flag=torch.zeros(1, dtype=torch.int32, device=dev),
+                 one=torch.ones(1, dtype=torch.int32).pin_memory())
         _BUF.clear()                      # keep one frame shape resident
         _BUF[key] = B
     if extras and not B["extras"]:

@@ -24,7 +24,7 @@ EXPORTS = (
     "schw_last_kernel_ms", "schw_integrate_batch", "schw_integrate_batch_dev", "schw_integrate_batch_full", "schw_integrate_batch_rows",
     "schw_initial_conditions", "schw_initial_conditions_px", "schw_classify", "schw_render", "schw_render_dev", "schw_last_total_steps",
     "schw_flat_render", "schw_fp64_peak_probe", "schw_math_probe", "schw_last_counters",
-    "schw_host_alloc", "schw_host_free",
+    "schw_host_alloc", "schw_host_free", "schw_set_tex_ready_flag",
 )
 
 
@@ -96,6 +96,7 @@ def load():
     L.schw_flat_render.argtypes = [vp, scp, vp, vp]
     L.schw_math_probe.argtypes = [vp, dp, i64, dp, dp, dp]
     L.schw_fp64_peak_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.schw_set_tex_ready_flag.argtypes = [vp, vp]
     L.schw_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.schw_host_free.argtypes = [vp]
     for name in EXPORTS:
@@ -332,8 +333,11 @@ class Handle:
         return out
 
     def render_dev(self, scene, d_tex, row_begin, row_end, row_stride, d_rgb, d_cls, stream=0,
-                   d_final_q=0, d_ic=0, d_hit=0, d_texel=0, d_nsteps=0):
-        """Device-pointer render: enqueue only (pointers are e.g. torch tensors' data_ptr())."""
+                   d_final_q=0, d_ic=0, d_hit=0, d_texel=0, d_nsteps=0, d_tex_ready=0):
+        """Device-pointer render: enqueue only (pointers are e.g. torch tensors' data_ptr()).
+        d_tex_ready: optional device uint32 the kernel waits on before its first texel lookup (schw_set_tex_ready_flag)."""
+        if d_tex_ready:
+            _check(self._L.schw_set_tex_ready_flag(self._h, C.c_void_p(d_tex_ready)))
         x = SchwRayOutputs(d_final_q or None, d_ic or None, d_hit or None, d_texel or None, d_nsteps or None)
         _check(self._L.schw_render_dev(self._h, C.byref(scene), C.c_void_p(d_tex or None), row_begin, row_end,
                                        row_stride, C.c_void_p(d_rgb), C.c_void_p(d_cls), C.byref(x),

@@ -46,6 +46,13 @@ def _worker(rank, world, port, h, w, q):
                   and np.array_equal(got["final_q"], ref["final_q"], equal_nan=True)
                   and np.array_equal(got["ic"], ref["ic"]) and np.array_equal(got["uv"], ref["uv"])
                   and np.array_equal(got["nsteps"], ref["nsteps"]) and got["rgb"].any())
+        # root=0: a gather instead of the all_gather -- rank 0 gets the same frame, the others nothing
+        got0 = render_frame(sc, tex, extras=True, handle=hd, root=0)
+        if rank == 0:
+            ok = ok and all(np.array_equal(got0[k], got[k], equal_nan=(k == "final_q"))
+                            for k in ("rgb", "cls", "final_q", "ic", "hit", "uv", "nsteps"))
+        else:
+            ok = ok and got0["rgb"] is None and got0["cls"] is None and got0["final_q"] is None
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
