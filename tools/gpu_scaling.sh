@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 TAG=${1:-r01}
 NG=$(nvidia-smi -L | wc -l)
-timeout 600 python -m pytest tests/test_gpu_multirank.py -q 2>&1 | tail -2
+[ -n "$SKIP_TESTS" ] || timeout 600 python -m pytest tests/test_gpu_multirank.py -q 2>&1 | tail -2
 for N in 1 2 4 8; do
   [ $N -gt $NG ] && break
   if [ $N -eq 1 ]; then
