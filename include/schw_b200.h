@@ -185,6 +185,12 @@ int  schw_fp64_peak_probe(schw_handle *h, double *tflops, float *ms);
  * simulation/cuda_geodesic.py:433-474) on n host values, for accuracy tests. */
 int  schw_math_probe(schw_handle *h, const double *x, int64_t n, double *rcp, double *sn, double *cs);
 
+/* Diagnostic, needs no device: the step parameters exactly as the kernels receive them (csrc/schw_device.cuh:
+ * StepParams, incl. the thresholds of the planar fast path), for the host-compiled model of the step loop in
+ * tests/model/.  out may be NULL to query the size. */
+int  schw_debug_step_params(int64_t steps, double delta, double rs, double r_max, double omega,
+                            void *out, size_t cap, size_t *size);
+
 #ifdef __cplusplus
 }
 #endif

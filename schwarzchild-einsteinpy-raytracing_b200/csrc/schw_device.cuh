@@ -16,7 +16,11 @@
 // states and bit-exact on class / texel (tests/).
 #pragma once
 #include <cstdint>
+#ifndef SCHW_HOST_MODEL
 #include <cuda_runtime.h>
+#endif
+// SCHW_HOST_MODEL: tests/model/planar_model.cpp compiles this header with g++ (one lane = one "warp", shims for the
+// few intrinsics) to check the planar fast path against the general flow on the CPU over many parameter sets.
 
 namespace schw {
 
@@ -84,7 +88,11 @@ struct RayState {
 __device__ __forceinline__ double fast_rcp(double x)
 {
     double y;
+#ifdef SCHW_HOST_MODEL
+    y = __hiloint2double(__double2hiint(1.0 / x), 0);     // stand-in for the ~2^-20 hardware seed
+#else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#endif
     double e = fma(-x, y, 1.0);
     e = fma(e, e, e);
     return fma(y, e, y);

@@ -918,6 +918,22 @@ static int make_scene_params(const schw_scene *s, int row_begin, int row_end, in
     return SCHW_OK;
 }
 
+// Diagnostic (no device needed): the step parameters -- incl. the thresholds of the planar fast path and of the
+// termination pre-test -- exactly as the kernels receive them, copied to `out` (sizeof(schw::StepParams) bytes).
+extern "C" int schw_debug_step_params(int64_t steps, double delta, double rs, double r_max, double omega,
+                                      void *out, size_t cap, size_t *size)
+{
+    StepParams P;
+    int rc = make_step_params(steps, delta, rs, r_max, omega, P);
+    if (rc) return rc;
+    if (size) *size = sizeof(P);
+    if (out) {
+        if (cap < sizeof(P)) return fail(SCHW_E_INVALID, "schw_debug_step_params: buffer too small");
+        memcpy(out, &P, sizeof(P));
+    }
+    return SCHW_OK;
+}
+
 static void begin_timed(schw_handle *h, cudaStream_t st)
 {
     cudaEventRecord(h->ev0, st);

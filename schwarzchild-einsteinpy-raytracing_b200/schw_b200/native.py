@@ -24,7 +24,7 @@ EXPORTS = (
     "schw_last_kernel_ms", "schw_integrate_batch", "schw_integrate_batch_dev", "schw_integrate_batch_full", "schw_integrate_batch_rows",
     "schw_initial_conditions", "schw_initial_conditions_px", "schw_classify", "schw_render", "schw_render_dev", "schw_last_total_steps",
     "schw_flat_render", "schw_fp64_peak_probe", "schw_math_probe", "schw_last_counters",
-    "schw_host_alloc", "schw_host_free", "schw_set_tex_ready_flag",
+    "schw_host_alloc", "schw_host_free", "schw_set_tex_ready_flag", "schw_debug_step_params",
 )
 
 
@@ -97,6 +97,7 @@ def load():
     L.schw_math_probe.argtypes = [vp, dp, i64, dp, dp, dp]
     L.schw_fp64_peak_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.schw_set_tex_ready_flag.argtypes = [vp, vp]
+    L.schw_debug_step_params.argtypes = [i64, dbl, dbl, dbl, dbl, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.schw_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.schw_host_free.argtypes = [vp]
     for name in EXPORTS:
