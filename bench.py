@@ -7,8 +7,8 @@
 Workload (BASELINE.json configs[3], the configuration its metric is quoted on): one 3840x2160 frame of the
 default config.py scene (observer (30,0,0), fov 80 deg, r_s = 2, r_max = 31, delta = 0.01, step cap 200 000,
 omega_eff = 1.0, full-sky patch) over a synthetic sky texture.  A "step" is one frame.  With N ranks the
-pixel rows are sharded row-cyclically (fixed total work => "strong" scaling) and each step ends with ONE
-all_gather of rgb+class over NCCL.
+pixel rows are sharded row-cyclically (fixed total work => "strong" scaling) and each step ends with ONE NCCL
+collective of rgb+class (all_gather in the device-timed leg, gather to rank 0 in the end-to-end leg).
 
 One JSON line on rank 0.  `value` = geodesic steps/s with inputs resident in HBM (CUDA events on the launch
 stream, max over ranks); `e2e` = the same metric through the host-buffer C-ABI call (pinned host texture in,

@@ -53,6 +53,8 @@ def test_no_gpu_means_loud_failure_not_fallback():
     with pytest.raises(schw_b200.SchwError) as e:
         schw_b200.Handle()
     assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    with pytest.raises(schw_b200.SchwError):             # page-locked frame buffers need the driver too: no pageable stand-in
+        schw_b200.native.pinned_empty((4, 4, 3), "uint8")
     from simulation.cuda_geodesic import CUDASchwarzschildIntegrator
     import numpy as np
     with pytest.raises(schw_b200.SchwError):
