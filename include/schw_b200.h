@@ -155,6 +155,24 @@ int  schw_render_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_t
                      int row_begin, int row_end, int row_stride,
                      uint8_t *d_rgb, uint8_t *d_cls, const schw_ray_outputs *d_extra,
                      void *cuda_stream);
+/* ---- next rows (opt-in): geodesic de-duplication -------------------------------
+ * Same arguments, same outputs -- bit for bit -- as schw_render / schw_render_dev.  Every camera ray of the reference
+ * starts at the same q0 with a 4-momentum that depends only on its angle alpha to the optical axis (simulation/utils.py:
+ * 148-194, 39-88), so pixels whose alpha agrees bitwise (mirror images and more: 8.3 M pixels of a 4K frame hold 0.95 M
+ * distinct values) own the same geodesic; each distinct one is integrated once and every pixel applies its own rotation
+ * by beta, classification and texel lookup (simulation/raytracing.py:181-273) to the shared final state.  The reference
+ * integrates every pixel; this entry point is therefore opt-in and reports its own counters: schw_last_total_steps =
+ * steps actually integrated, schw_last_dedup_stats = distinct rays and the steps summed over pixels.
+ * The _dev variant synchronises its stream once (the distinct-ray count sizes the second half of the pipeline). */
+int  schw_render_dedup(schw_handle *h, const schw_scene *scene, const uint8_t *tex,
+                       int row_begin, int row_end, int row_stride,
+                       uint8_t *rgb, uint8_t *cls, const schw_ray_outputs *extra);
+int  schw_render_dedup_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex,
+                           int row_begin, int row_end, int row_stride,
+                           uint8_t *d_rgb, uint8_t *d_cls, const schw_ray_outputs *d_extra,
+                           void *cuda_stream);
+int  schw_last_dedup_stats(schw_handle *h, uint64_t *unique_rays, uint64_t *pixel_steps);
+
 /* Overlap of the texture upload with the start of a frame (optional, one-shot): the next schw_render_dev call on this
  * handle may be enqueued BEFORE its texture has arrived in d_tex; the kernel waits -- per ray, only at the texel lookup
  * that ends it -- until the 32-bit word at d_flag is non-zero.  The caller clears the word, uploads the texture on

@@ -468,6 +468,7 @@ __device__ __forceinline__ double pymod(double a, double b)
 // ---------------------------------------------------------------------------------------------
 struct RayIC {
     double p0[4];
+    double alpha;      // camera angle pi - h_phi: p0 is a function of it alone (key of the geodesic de-duplication)
     double alpha0, beta;
     double dir[3];     // normalised un-rotated ray (for the diagnostic h_r,h_theta,h_phi)
 };
@@ -494,6 +495,7 @@ __device__ __forceinline__ void initial_conditions_px(const SceneParams &sc, dou
     const double disc = sc.m4A * C;
     ic.p0[0] = sqrt(disc) / sc.twomA;
     ic.p0[1] = pr; ic.p0[2] = pth; ic.p0[3] = pph;
+    ic.alpha = alpha;
     ic.alpha0 = acos(-pr / sc.f_r);
     ic.beta = beta;
     ic.dir[0] = d0; ic.dir[1] = d1; ic.dir[2] = d2;

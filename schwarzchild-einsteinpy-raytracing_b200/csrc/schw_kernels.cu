@@ -24,6 +24,9 @@
 #include <algorithm>
 #include <utility>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "schw_device.cuh"
 #include "../../include/schw_b200.h"
 
@@ -51,6 +54,7 @@ struct Counters {
     unsigned long long planar_iters; // of those, completed entirely on the planar fast path
     int batch_planar;                // verdict of batch_probe_kernel
     int _pad;
+    unsigned long long pixel_steps;  // de-duplicated render: steps summed over PIXELS (what one ray per pixel would take)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -457,6 +461,77 @@ batch_probe_kernel(const double *__restrict__ q0s, const double *__restrict__ p0
 }
 
 // ---------------------------------------------------------------------------------------------
+// Geodesic de-duplication (opt-in: schw_render_dedup*).  Every camera ray starts at the same q0 with
+// p0 = F(alpha), alpha = its angle to the optical axis (utils.py:148-194), so pixels whose alpha agrees BITWISE -- the
+// mirror images of a pixel, and more -- own the same geodesic: 8.3 M pixels of a 4K frame hold 0.95 M distinct alphas.
+// The frame is rendered exactly as without it (same bits in every output), integrating each distinct ray once:
+//   keys (alpha bits per pixel) -> radix sort -> run heads -> one integrate_batch over the distinct rays
+//   -> per-pixel epilogue (own beta: rotate back, classify, texel) reading its geodesic's final state.
+// ---------------------------------------------------------------------------------------------
+__global__ void dedup_key_kernel(const __grid_constant__ SceneParams sc, long long n, unsigned long long *__restrict__ keys,
+                                 unsigned *__restrict__ pix)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int row = (int)(k / sc.width), j = (int)(k - (long long)row * sc.width);
+    RayIC r;
+    initial_conditions(sc, sc.row_begin + row * sc.row_stride, j, r);
+    keys[k] = (unsigned long long)__double_as_longlong(r.alpha);
+    pix[k] = (unsigned)k;
+}
+
+__global__ void dedup_heads_kernel(const unsigned long long *__restrict__ keys_sorted, long long n, int *__restrict__ head)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    head[i] = (i == 0 || keys_sorted[i] != keys_sorted[i - 1]) ? 1 : 0;
+}
+
+// uid1[i] = inclusive sum of head[] = 1-based index of the distinct ray of sorted position i
+__global__ void dedup_scatter_kernel(const __grid_constant__ SceneParams sc, long long n, const unsigned *__restrict__ pix_sorted,
+                                     const int *__restrict__ head, const int *__restrict__ uid1, int *__restrict__ ray_of_pixel,
+                                     double *__restrict__ uq0, double *__restrict__ up0)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = pix_sorted[i];
+    const int u = uid1[i] - 1;
+    ray_of_pixel[k] = u;
+    if (head[i]) {
+        const int row = (int)(k / sc.width), j = (int)(k - (long long)row * sc.width);
+        RayIC r;
+        initial_conditions(sc, sc.row_begin + row * sc.row_stride, j, r);
+        double2 *q = reinterpret_cast<double2 *>(uq0 + 4 * (size_t)u), *p = reinterpret_cast<double2 *>(up0 + 4 * (size_t)u);
+        q[0] = make_double2(0.0, sc.r_obs); q[1] = make_double2(sc.th_obs, sc.ph_obs);
+        p[0] = make_double2(r.p0[0], r.p0[1]); p[1] = make_double2(r.p0[2], r.p0[3]);
+    }
+}
+
+// per pixel: its own (alpha0, beta) again, the final state of its geodesic, then the same epilogue as the fused kernel
+__global__ void __launch_bounds__(kBlock)
+dedup_epilogue_kernel(const __grid_constant__ RenderJob job, const int *__restrict__ ray_of_pixel,
+                      const double *__restrict__ ufq, const int32_t *__restrict__ unsteps, Counters *ctr)
+{
+    __shared__ double2 s_stage[4 * kBlock];
+    __shared__ unsigned long long s_steps;
+    if (threadIdx.x == 0) s_steps = 0ull;
+    __syncthreads();
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < job.n) {
+        double2 slot;
+        job.load(k, &s_stage[threadIdx.x], slot);           // writes ic[k] if requested; slot = (alpha0, beta)
+        const int u = ray_of_pixel[k];
+        const double2 a = *reinterpret_cast<const double2 *>(ufq + 4 * (size_t)u);
+        const double2 b = *reinterpret_cast<const double2 *>(ufq + 4 * (size_t)u + 2);
+        const int ns = unsteps[u];
+        job.store(k, a.x, a.y, b.x, b.y, ns, !(a.y == a.y), slot);
+        atomicAdd(&s_steps, (unsigned long long)ns);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_steps) atomicAdd(&ctr->pixel_steps, s_steps);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stage kernels (boundary / parity testing): one thread per ray, static mapping.
 // ---------------------------------------------------------------------------------------------
 __global__ void ic_kernel(const __grid_constant__ SceneParams sc, long long n, double *__restrict__ q0s,
@@ -643,6 +718,9 @@ struct schw_handle {
     int occ_render[3] = {0, 0, 0}, occ_batch[3] = {0, 0, 0};   // filled on first use, see launch_persistent
     // grow-only scratch
     DevBuf in_a, in_b, in_c, tex, rgb, cls, fq, ic, hit, texel, nsteps, traj, rows, order;
+    DevBuf dd_keys, dd_keys2, dd_pix, dd_pix2, dd_head, dd_uid, dd_map, dd_tmp, dd_q0, dd_p0, dd_fq, dd_ns;   // de-duplication
+    bool in_pipeline = false;             // a multi-kernel entry point owns the timing events and the counters
+    long long last_unique = 0;            // distinct rays of the last de-duplicated render
     double order_key[12] = {0};   // camera geometry the cached tile order was built for
     long long order_tiles = 0;
 };
@@ -709,7 +787,9 @@ extern "C" int schw_destroy(schw_handle *h)
     if (!h) return SCHW_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->in_a, &h->in_b, &h->in_c, &h->tex, &h->rgb, &h->cls, &h->fq, &h->ic, &h->hit, &h->texel, &h->nsteps, &h->traj, &h->rows, &h->order};
+    DevBuf *bufs[] = {&h->in_a, &h->in_b, &h->in_c, &h->tex, &h->rgb, &h->cls, &h->fq, &h->ic, &h->hit, &h->texel, &h->nsteps, &h->traj, &h->rows, &h->order,
+                      &h->dd_keys, &h->dd_keys2, &h->dd_pix, &h->dd_pix2, &h->dd_head, &h->dd_uid, &h->dd_map, &h->dd_tmp,
+                      &h->dd_q0, &h->dd_p0, &h->dd_fq, &h->dd_ns};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     if (h->ctr) cudaFree(h->ctr);
     if (h->tex_flag) cudaFree(h->tex_flag);
@@ -936,12 +1016,14 @@ extern "C" int schw_debug_step_params(int64_t steps, double delta, double rs, do
 
 static void begin_timed(schw_handle *h, cudaStream_t st)
 {
+    if (h->in_pipeline) return;
     cudaEventRecord(h->ev0, st);
     h->launches = 0;
     h->last_stream = st;
 }
 static void end_timed(schw_handle *h, cudaStream_t st)
 {
+    if (h->in_pipeline) return;
     cudaEventRecord(h->ev1, st);
     h->timed = true;
 }
@@ -1386,6 +1468,143 @@ extern "C" int schw_render(schw_handle *h, const schw_scene *scene, const uint8_
         if (d.nsteps) CU(cudaMemcpyAsync(x->nsteps, d.nsteps, n * 4, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
+    return SCHW_OK;
+}
+
+// ---- de-duplicated render (N4, opt-in) ------------------------------------------------------------
+// Same contract and same output bits as schw_render_dev, but pixels whose camera angle agrees bitwise share one
+// integration (see dedup_key_kernel).  Unlike schw_render_dev it synchronises the stream once in the middle (the number
+// of distinct rays sizes the second half), so it is not enqueue-only.
+extern "C" int schw_render_dedup_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex, int row_begin,
+                                     int row_end, int row_stride, uint8_t *d_rgb, uint8_t *d_cls,
+                                     const schw_ray_outputs *x, void *cuda_stream)
+{
+    if (!h || !scene) return fail(SCHW_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    SceneParams sc;
+    int rc = make_scene_params(scene, row_begin, row_end, row_stride, sc);
+    if (rc) return rc;
+    if (scene->has_texture && !d_tex) return fail(SCHW_E_INVALID, "has_texture set but tex is NULL");
+    const long long n = (long long)sc.nrows * sc.width;
+    if (n > 0x7fffffffLL) return fail(SCHW_E_INVALID, "more than 2^31-1 rays");
+    if (n > 0 && (!d_rgb || !d_cls)) return fail(SCHW_E_INVALID, "null output");
+    {   // validate the step parameters before any work is enqueued
+        StepParams P;
+        rc = make_step_params(scene->steps, scene->delta, 2.0 * scene->mass, scene->r_max, scene->omega, P);
+        if (rc) return rc;
+    }
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    begin_timed(h, st);
+    h->last_unique = 0;
+    if (n == 0) { CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st)); end_timed(h, st); return SCHW_OK; }
+
+    // 1. keys -> sort -> run heads -> distinct-ray index of every pixel
+    ENSURE(h->dd_keys, (size_t)n * 8); ENSURE(h->dd_keys2, (size_t)n * 8);
+    ENSURE(h->dd_pix, (size_t)n * 4); ENSURE(h->dd_pix2, (size_t)n * 4);
+    ENSURE(h->dd_head, (size_t)n * 4); ENSURE(h->dd_uid, (size_t)n * 4); ENSURE(h->dd_map, (size_t)n * 4);
+    auto *keys = (unsigned long long *)h->dd_keys.p, *keys2 = (unsigned long long *)h->dd_keys2.p;
+    auto *pix = (unsigned *)h->dd_pix.p, *pix2 = (unsigned *)h->dd_pix2.p;
+    int *head = (int *)h->dd_head.p, *uid1 = (int *)h->dd_uid.p, *map = (int *)h->dd_map.p;
+    size_t tmp_sort = 0, tmp_scan = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys2, pix, pix2, (int)n, 0, 64, st));
+    CU(cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, head, uid1, (int)n, st));
+    ENSURE(h->dd_tmp, tmp_sort > tmp_scan ? tmp_sort : tmp_scan);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    dedup_key_kernel<<<blocks, 256, 0, st>>>(sc, n, keys, pix);
+    CU(cudaGetLastError());
+    size_t tmp = h->dd_tmp.cap;
+    CU(cub::DeviceRadixSort::SortPairs(h->dd_tmp.p, tmp, keys, keys2, pix, pix2, (int)n, 0, 64, st));
+    dedup_heads_kernel<<<blocks, 256, 0, st>>>(keys2, n, head);
+    CU(cudaGetLastError());
+    tmp = h->dd_tmp.cap;
+    CU(cub::DeviceScan::InclusiveSum(h->dd_tmp.p, tmp, head, uid1, (int)n, st));
+    int n_unique = 0;
+    CU(cudaMemcpyAsync(&n_unique, uid1 + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_unique <= 0 || n_unique > n) return fail(SCHW_E_CUDA, "de-duplication produced an impossible ray count");
+    h->last_unique = n_unique;
+
+    // 2. the distinct rays, integrated once each
+    ENSURE(h->dd_q0, (size_t)n_unique * 32); ENSURE(h->dd_p0, (size_t)n_unique * 32);
+    ENSURE(h->dd_fq, (size_t)n_unique * 32); ENSURE(h->dd_ns, (size_t)n_unique * 4);
+    dedup_scatter_kernel<<<blocks, 256, 0, st>>>(sc, n, pix2, head, uid1, map, (double *)h->dd_q0.p, (double *)h->dd_p0.p);
+    CU(cudaGetLastError());
+    h->launches += 5;                                   // key, sort, heads, scan, scatter
+    h->in_pipeline = true;
+    rc = integrate_batch_impl(h, (const double *)h->dd_q0.p, (const double *)h->dd_p0.p, n_unique, scene->steps, scene->delta,
+                              2.0 * scene->mass, scene->r_max, scene->omega, (double *)h->dd_fq.p, (int32_t *)h->dd_ns.p, st);
+    h->in_pipeline = false;
+    if (rc) return rc;
+
+    // 3. per-pixel epilogue
+    RenderJob job;
+    job.sc = sc; job.tex = d_tex; job.tex_ready = nullptr; job.rgb = d_rgb; job.cls = d_cls;
+    job.final_q = x ? x->final_q : nullptr;
+    job.ic = x ? x->ic : nullptr;
+    job.hit = x ? x->hit : nullptr;
+    job.texel = x ? x->texel : nullptr;
+    job.nsteps = x ? x->nsteps : nullptr;
+    job.n = n;
+    job.tile_order = nullptr; job.tiles_per_row = 1; job.qlen = n;
+    dedup_epilogue_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, st>>>(job, map, (const double *)h->dd_fq.p,
+                                                                                  (const int32_t *)h->dd_ns.p, h->ctr);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    end_timed(h, st);
+    return SCHW_OK;
+}
+
+extern "C" int schw_render_dedup(schw_handle *h, const schw_scene *scene, const uint8_t *tex, int row_begin, int row_end,
+                                 int row_stride, uint8_t *rgb, uint8_t *cls, const schw_ray_outputs *x)
+{
+    if (!h || !scene) return fail(SCHW_E_INVALID, "null argument");
+    if (scene->height <= 0 || scene->width <= 0) return fail(SCHW_E_INVALID, "image_size must be positive");
+    if (row_stride <= 0 || row_begin < 0 || row_end > scene->height || row_begin > row_end)
+        return fail(SCHW_E_INVALID, "bad row range");
+    if (scene->has_texture && !tex) return fail(SCHW_E_INVALID, "has_texture set but tex is NULL");
+    CU(cudaSetDevice(h->device));
+    const int nrows = row_end > row_begin ? (row_end - row_begin + row_stride - 1) / row_stride : 0;
+    const size_t n = (size_t)nrows * scene->width;
+    if (n > 0 && (!rgb || !cls)) return fail(SCHW_E_INVALID, "null output");
+    cudaStream_t st = h->stream;
+    const size_t tb = (size_t)scene->height * scene->width * 3;
+    if (scene->has_texture) { ENSURE(h->tex, tb); CU(cudaMemcpyAsync(h->tex.p, tex, tb, cudaMemcpyHostToDevice, st)); }
+    ENSURE(h->rgb, n * 3 + 1); ENSURE(h->cls, n + 1);
+    schw_ray_outputs d = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (x) {
+        if (x->final_q) { ENSURE(h->fq, n * 32); d.final_q = (double *)h->fq.p; }
+        if (x->ic) { ENSURE(h->ic, n * 72); d.ic = (double *)h->ic.p; }
+        if (x->hit) { ENSURE(h->hit, n * 16); d.hit = (double *)h->hit.p; }
+        if (x->texel) { ENSURE(h->texel, n * 8); d.texel = (int32_t *)h->texel.p; }
+        if (x->nsteps) { ENSURE(h->nsteps, n * 4); d.nsteps = (int32_t *)h->nsteps.p; }
+    }
+    int rc = schw_render_dedup_dev(h, scene, scene->has_texture ? (const uint8_t *)h->tex.p : nullptr, row_begin, row_end,
+                                   row_stride, (uint8_t *)h->rgb.p, (uint8_t *)h->cls.p, &d, nullptr);
+    if (rc) return rc;
+    if (n > 0) {
+        CU(cudaMemcpyAsync(rgb, h->rgb.p, n * 3, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(cls, h->cls.p, n, cudaMemcpyDeviceToHost, st));
+        if (d.final_q) CU(cudaMemcpyAsync(x->final_q, d.final_q, n * 32, cudaMemcpyDeviceToHost, st));
+        if (d.ic) CU(cudaMemcpyAsync(x->ic, d.ic, n * 72, cudaMemcpyDeviceToHost, st));
+        if (d.hit) CU(cudaMemcpyAsync(x->hit, d.hit, n * 16, cudaMemcpyDeviceToHost, st));
+        if (d.texel) CU(cudaMemcpyAsync(x->texel, d.texel, n * 8, cudaMemcpyDeviceToHost, st));
+        if (d.nsteps) CU(cudaMemcpyAsync(x->nsteps, d.nsteps, n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return SCHW_OK;
+}
+
+// Distinct rays integrated by the last schw_render_dedup* call, and the steps summed over its pixels (what one ray
+// per pixel would have taken; schw_last_total_steps reports the steps actually integrated).
+extern "C" int schw_last_dedup_stats(schw_handle *h, uint64_t *unique_rays, uint64_t *pixel_steps)
+{
+    if (!h) return fail(SCHW_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    Counters c;
+    CU(cudaStreamSynchronize(h->last_stream ? h->last_stream : h->stream));
+    CU(cudaMemcpy(&c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost));
+    if (unique_rays) *unique_rays = (uint64_t)h->last_unique;
+    if (pixel_steps) *pixel_steps = c.pixel_steps;
     return SCHW_OK;
 }
 

@@ -25,6 +25,7 @@ EXPORTS = (
     "schw_initial_conditions", "schw_initial_conditions_px", "schw_classify", "schw_render", "schw_render_dev", "schw_last_total_steps",
     "schw_flat_render", "schw_fp64_peak_probe", "schw_math_probe", "schw_last_counters",
     "schw_host_alloc", "schw_host_free", "schw_set_tex_ready_flag", "schw_debug_step_params",
+    "schw_render_dedup", "schw_render_dedup_dev", "schw_last_dedup_stats",
 )
 
 
@@ -93,6 +94,9 @@ def load():
     L.schw_classify.argtypes = [vp, scp, dp, dp, dp, i64, vp, vp, vp, dp, vp]
     L.schw_render.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop]
     L.schw_render_dev.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop, vp]
+    L.schw_render_dedup.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop]
+    L.schw_render_dedup_dev.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop, vp]
+    L.schw_last_dedup_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.schw_flat_render.argtypes = [vp, scp, vp, vp]
     L.schw_math_probe.argtypes = [vp, dp, i64, dp, dp, dp]
     L.schw_fp64_peak_probe.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
@@ -312,8 +316,15 @@ class Handle:
         return dict(rgb=rgb, cls=cls, hit=hit, uv=uv)
 
     # -- fused render -----------------------------------------------------------------------------
-    def render(self, scene, tex, row_begin=0, row_end=None, row_stride=1, extras=False):
-        """Host-buffer render (H2D of the texture and D2H of the outputs happen inside the call)."""
+    def last_dedup_stats(self):
+        """(distinct rays, steps summed over pixels) of the last render(..., dedup=True)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(self._L.schw_last_dedup_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def render(self, scene, tex, row_begin=0, row_end=None, row_stride=1, extras=False, dedup=False):
+        """Host-buffer render (H2D of the texture and D2H of the outputs happen inside the call).
+        dedup=True (opt-in): pixels with bitwise equal camera angle share one integration; same outputs."""
         row_end = scene.height if row_end is None else row_end
         nrows = len(range(row_begin, row_end, row_stride))
         w = scene.width
@@ -329,8 +340,9 @@ class Handle:
                        uv=np.zeros((n, 2), np.int32), nsteps=np.zeros(n, np.int32))
             x = SchwRayOutputs(out["final_q"].ctypes.data, out["ic"].ctypes.data, out["hit"].ctypes.data,
                                out["uv"].ctypes.data, out["nsteps"].ctypes.data)
-        _check(self._L.schw_render(self._h, C.byref(scene), _p(tex), row_begin, row_end, row_stride,
-                                   _p(rgb), _p(cls), C.byref(x) if x is not None else None))
+        fn = self._L.schw_render_dedup if dedup else self._L.schw_render
+        _check(fn(self._h, C.byref(scene), _p(tex), row_begin, row_end, row_stride,
+                  _p(rgb), _p(cls), C.byref(x) if x is not None else None))
         return out
 
     def render_dev(self, scene, d_tex, row_begin, row_end, row_stride, d_rgb, d_cls, stream=0,

@@ -1,0 +1,41 @@
+"""Opt-in geodesic de-duplication (schw_render_dedup): pixels whose camera angle agrees bitwise share one
+integration.  It must reproduce the one-ray-per-pixel render in every output bit, while integrating several times
+fewer rays."""
+import numpy as np
+import pytest
+
+from helpers import synthetic_sky
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+@pytest.mark.parametrize("kw,rows,max_share", [
+    (dict(height=270, width=480), (0, None, 1), 0.5),
+    (dict(height=135, width=135), (0, None, 1), 0.5),                       # odd: exactly radial centre ray
+    (dict(height=200, width=200, delta=0.05, steps=300), (0, None, 1), 0.5),  # step cap -> in_domain
+    (dict(height=96, width=160, patch_center_phi=2.0, patch_size_phi=1.5, patch_size_theta=1.0, flip_phi=True), (0, None, 1), 0.5),
+    # one rank's row-cyclic shard: the vertical mirror image of its rows belongs to another rank, the horizontal one stays
+    (dict(height=216, width=384), (1, 216, 4), 0.75),
+], ids=["default", "odd", "cap", "patch", "shard"])
+def test_dedup_render_is_bit_identical(handle, kw, rows, max_share):
+    import schw_b200
+    sc = schw_b200.make_scene(**kw)
+    tex = synthetic_sky(sc.height, sc.width, seed=4)
+    rb, re, rs = rows
+    a = handle.render(sc, tex, rb, re, rs, extras=True)
+    steps_full = handle.last_total_steps()
+    b = handle.render(sc, tex, rb, re, rs, extras=True, dedup=True)
+    steps_dedup = handle.last_total_steps()
+    unique, pixel_steps = handle.last_dedup_stats()
+    for key in ("rgb", "cls", "final_q", "ic", "hit", "uv", "nsteps"):
+        assert np.array_equal(_bits(a[key]), _bits(b[key])), key
+    n = a["cls"].size
+    assert pixel_steps == steps_full == int(a["nsteps"].astype(np.int64).sum())
+    assert 0 < unique < max_share * n and steps_dedup < max_share * steps_full, (unique, n, steps_dedup, steps_full)
+    # without the diagnostics too
+    c = handle.render(sc, tex, rb, re, rs, dedup=True)
+    assert np.array_equal(c["rgb"], a["rgb"]) and np.array_equal(c["cls"], a["cls"])
