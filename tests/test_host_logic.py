@@ -124,3 +124,22 @@ def test_pinned_frame_buffers_are_plain_arrays_and_recycled(monkeypatch):
     assert native.pinned_empty((0, 3), np.uint8).shape == (0, 3)
     for addr in native._PINNED_POOL.pop(60):
         libc.free(addr)
+
+
+def test_camera_rays_repeat_bitwise_premise_of_the_dedup_render(orc):
+    """Premise of the opt-in de-duplicated render (schw_render_dedup), checked with the oracle's restatement
+    of get_initial_conditions: the 4-momentum of a camera ray is a function of its camera angle alone and the pixel grid
+    is mirror symmetric, so a frame holds several times fewer DISTINCT (q0, p0) than pixels -- bit for bit."""
+    for (h, w), min_ratio in (((400, 400), 10.0), ((108, 192), 6.5), ((135, 135), 8.0)):
+        sc = orc.make_scene(height=h, width=w)
+        ii, jj = np.mgrid[0:h, 0:w]
+        px = orc.camera_pixels(sc, np.stack([ii.ravel(), jj.ravel()], 1).astype(np.int32))
+        q0s, ic, rc = orc.initial_conditions(np.array([30.0, 0.0, 0.0]), px, 1.0)
+        assert rc == 0 and len(np.unique(q0s.view(np.int64), axis=0)) == 1
+        p0 = np.ascontiguousarray(ic[:, 0:4])
+        distinct = len(np.unique(p0.view(np.int64), axis=0))
+        assert h * w / distinct >= min_ratio, (h, w, distinct)
+        # most mirror images of a pixel carry the same momentum bit for bit -- not all: (j + 0.5) / w - 0.5 does not round
+        # symmetrically -- which is why the render keys on the bits themselves instead of assuming the symmetry
+        P = p0.reshape(h, w, 4).view(np.int64)
+        assert 0.9 < (P == P[::-1]).all(-1).mean() < 1.0 and 0.9 < (P == P[:, ::-1]).all(-1).mean() < 1.0
