@@ -356,6 +356,15 @@ class Handle:
                                        row_stride, C.c_void_p(d_rgb), C.c_void_p(d_cls), C.byref(x),
                                        C.c_void_p(stream or None)))
 
+    def render_dedup_dev(self, scene, d_tex, row_begin, row_end, row_stride, d_rgb, d_cls, stream=0,
+                         d_final_q=0, d_ic=0, d_hit=0, d_texel=0, d_nsteps=0):
+        """Device-pointer de-duplicated render (opt-in).  Synchronises the stream once unless the
+        geodesics of the previous call on this handle can be reused (same camera, rows and integrator parameters)."""
+        x = SchwRayOutputs(d_final_q or None, d_ic or None, d_hit or None, d_texel or None, d_nsteps or None)
+        _check(self._L.schw_render_dedup_dev(self._h, C.byref(scene), C.c_void_p(d_tex or None), row_begin, row_end,
+                                             row_stride, C.c_void_p(d_rgb), C.c_void_p(d_cls), C.byref(x),
+                                             C.c_void_p(stream or None)))
+
     def flat_render(self, scene, tex):
         tex = np.ascontiguousarray(tex, np.uint8)
         rgb = np.zeros((scene.height, scene.width, 3), np.uint8)
