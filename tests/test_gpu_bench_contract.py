@@ -31,6 +31,10 @@ def test_bench_line_small_frame():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 1e5 and "rows" in c["sample"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the opt-in de-duplicated render is reported beside the headline, never in it
+    dd = d["dedup_opt_in"]
+    assert dd["identical_to_one_ray_per_pixel"] is True and 0 < dd["distinct_rays"] < dd["pixels"] / 2
+    assert dd["pixel_steps"] == d["steps_per_frame"] and dd["steps_integrated"] < dd["pixel_steps"] / 2
 
 
 def test_bench_reference_arm_small_frame():
