@@ -143,3 +143,26 @@ def test_camera_rays_repeat_bitwise_premise_of_the_dedup_render(orc):
         # symmetrically -- which is why the render keys on the bits themselves instead of assuming the symmetry
         P = p0.reshape(h, w, 4).view(np.int64)
         assert 0.9 < (P == P[::-1]).all(-1).mean() < 1.0 and 0.9 < (P == P[:, ::-1]).all(-1).mean() < 1.0
+
+
+def test_dedup_is_exact_in_the_references_own_arithmetic(orc):
+    """The de-duplicated render as an algorithm, run entirely with the CPU restatement of the reference: integrate each
+    DISTINCT (q0, p0) once, give every pixel the final state of its geodesic and its own beta, classify -- and obtain
+    the frame the one-ray-per-pixel loop of run_manual_simulation produces, bit for bit (class, rgb, texel, final state).
+    The GPU pipeline (schw_render_dedup) has the same structure; tests/test_gpu_dedup.py checks it against the GPU render."""
+    from helpers import synthetic_sky
+    h, w = 60, 96
+    sc = orc.make_scene(height=h, width=w, delta=0.05, patch_center_phi=2.5, patch_size_phi=4.0, flip_phi=True)
+    tex = synthetic_sky(h, w, seed=3)
+    ref = orc.render(sc, tex, nthreads=2)
+    p0 = np.ascontiguousarray(ref["ic"][:, 0:4])
+    uniq, inv = np.unique(p0.view(np.int64), axis=0, return_inverse=True)
+    inv = inv.reshape(-1)
+    assert len(uniq) < h * w / 3
+    q0 = np.tile([0.0, 30.0, np.pi / 2, 0.0], (len(uniq), 1))
+    fq_u, ns_u = orc.integrate_batch(q0, uniq.view(np.float64), sc.steps, sc.delta, 2.0 * sc.mass, sc.r_max, 1.0)
+    fq = fq_u[inv]
+    got = orc.classify(sc, fq, ref["ic"][:, 4], ref["ic"][:, 5], tex)
+    assert np.array_equal(fq.view(np.int64), ref["final_q"].view(np.int64)) and np.array_equal(ns_u[inv], ref["nsteps"])
+    assert np.array_equal(got["cls"], ref["cls"].reshape(-1)) and np.array_equal(got["rgb"], ref["rgb"].reshape(-1, 3))
+    assert np.array_equal(got["uv"], ref["uv"]) and np.array_equal(got["hit"].view(np.int64), ref["hit"].view(np.int64))
