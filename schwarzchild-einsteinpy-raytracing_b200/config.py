@@ -38,6 +38,8 @@ _EXTRA_FLAGS = [
     ("--width", dict(type=int, default=None, help="[additive] frame width (default: --size)")),
     ("--height", dict(type=int, default=None, help="[additive] frame height (default: --size)")),
     ("--no-plots", dict(action="store_true", help="[additive] skip the matplotlib diagnostics (also skipped when matplotlib is absent)")),
+    ("--dedup", dict(action="store_true", help="[additive] integrate each distinct camera ray once (pixels whose camera angle agrees "
+                                               "bitwise share a geodesic); the image and the CSVs are identical, ~8x faster")),
 ]
 
 

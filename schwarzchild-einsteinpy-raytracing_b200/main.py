@@ -55,7 +55,7 @@ def main(argv=None):
         bh, observer, real_time=False, update_every=max(1, (image_size[0] * image_size[1]) // 32),
         steps=args.steps, delta=args.delta, omega=args.omega, rtol=args.rtol, atol=args.atol, order=args.order,
         suppress_warnings=args.suppress_warnings, background_path=args.background, use_cuda=args.cuda,
-        boundary_radius=args.boundary_radius, n_samples=20, **patch)
+        boundary_radius=args.boundary_radius, n_samples=20, dedup=args.dedup, **patch)
     img, photon_trajectories = result if isinstance(result, tuple) else (result, None)
     if rank != 0:
         return                                  # rank 0 owns the files and the summary

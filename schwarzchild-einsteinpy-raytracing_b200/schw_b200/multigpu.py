@@ -77,7 +77,7 @@ def _torch_stream_ptr():
     return p if p else 1
 
 
-def render_frame(scene, tex, extras=False, handle=None, root=None):
+def render_frame(scene, tex, extras=False, handle=None, root=None, dedup=False):
     """Render the whole frame of `scene`; sharded + gathered when torch.distributed is initialised.
 
     world == 1: the host-buffer C-ABI call.  world > 1: every rank uploads the texture on a side stream while its rows
@@ -85,6 +85,7 @@ def render_frame(scene, tex, extras=False, handle=None, root=None):
     first texel lookup), the packed (rows, 4w) u8 blocks are exchanged on the device with ONE NCCL collective and copied
     to page-locked host arrays.  root=None: all_gather, every rank returns the frame; root=r: gather, only rank r
     receives and returns it (the other ranks get rgb = cls = None) -- the frame then crosses PCIe once, not once per rank.
+    dedup=True (opt-in, single process only for now): the de-duplicated render, same outputs (schw_render_dedup).
 
     Returns dict(rgb (h,w,3) u8, cls (h,w) u8, q0 (4,)) plus, with extras, final_q (n,4), ic (n,9),
     hit (n,2), uv (n,2), nsteps (n,) in natural pixel order."""
@@ -96,7 +97,7 @@ def render_frame(scene, tex, extras=False, handle=None, root=None):
     q0, _ = hd.initial_conditions_px(np.array([scene.obs[0], scene.obs[1], scene.obs[2]]),
                                      np.zeros((1, 3)), scene.mass)
     if world == 1:
-        out = hd.render(scene, tex, rb, re, rs, extras=extras)
+        out = hd.render(scene, tex, rb, re, rs, extras=extras, dedup=dedup)
         res = dict(rgb=out["rgb"], cls=out["cls"], q0=q0[0])
         if extras:
             res.update({k: out[k] for k in ("final_q", "ic", "hit", "uv", "nsteps")})

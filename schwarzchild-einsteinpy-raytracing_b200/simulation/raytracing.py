@@ -57,11 +57,13 @@ def run_manual_simulation(
     flip_theta=False, flip_phi=False,
     n_samples=0,
     write_outputs=True,
+    dedup=False,
 ):
     """Render the lensed image; returns `img` (h,w,3) uint8, or `(img, sampled_trajectories)` when n_samples > 0.
 
     `real_time, update_every, omega, rtol, atol, order, suppress_warnings` are accepted and ignored,
-    as in the reference.  `write_outputs=False` (additive) skips the PNG/CSV side effects.
+    as in the reference (SURVEY App. D-1).  `write_outputs=False` (additive) skips the PNG/CSV side effects;
+    `dedup=True` (additive, single process) integrates each distinct camera ray once -- same image, same CSV columns.
     """
     logging.info("Starting manual ray tracing simulation...")
     h, w = observer.image_size
@@ -90,7 +92,7 @@ def run_manual_simulation(
                             patch_size_theta, patch_size_phi, flip_theta, flip_phi, bg_array is not None)
     logging.info("Using CUDA Schwarzschild integrator for curved rays ...")
     from schw_b200.multigpu import render_frame
-    out = render_frame(scene, bg_array, extras=True)
+    out = render_frame(scene, bg_array, extras=True, dedup=dedup)
     img = out["rgb"]
     cls = out["cls"].reshape(-1)
     ic = out["ic"]

@@ -141,3 +141,21 @@ def test_main_entry_point_end_to_end(tmp_path, monkeypatch, capsys):
     assert "Photon summary:" in out and f"Captured by BH: {(df['collision'] == 'bh').sum()}" in out
     sr = pd.read_csv("sampled_rays.csv")
     assert sr["ray_id"].nunique() == 20 and sr.groupby("ray_id").size().max() == 1000
+
+
+def test_main_entry_point_with_dedup_writes_the_same_frame_and_table(tmp_path, monkeypatch):
+    """`main.py --dedup` (additive flag): image and photon_data.csv identical to the default run."""
+    import pandas as pd
+    from PIL import Image
+    import main as entry
+    args = ["--size", "40", "--delta", "0.1", "--background", os.path.join(GOLDEN, "texture_card.png"), "--no-plots",
+            "--no-flat-trajectories"]
+    res = {}
+    for tag, extra in (("plain", []), ("dedup", ["--dedup"])):
+        d = tmp_path / tag
+        d.mkdir()
+        monkeypatch.chdir(d)
+        entry.main(args + extra)
+        res[tag] = (np.array(Image.open("images/manual_output.png").convert("RGB")), pd.read_csv("photon_data.csv"))
+    assert np.array_equal(res["plain"][0], res["dedup"][0]) and res["plain"][0].any()
+    pd.testing.assert_frame_equal(res["plain"][1], res["dedup"][1], check_exact=True)

@@ -22,8 +22,9 @@ def test_config_flags_and_defaults_match_reference():
     assert b.size == 400 and b.bg_flip_phi and b.boundary_radius == 21.0 and b.order == 4
     with pytest.raises(SystemExit):
         config.parse_args(["--order", "3"])
-    # additive flags default to the reference's behaviour (square frame)
-    assert a["width"] is None and a["height"] is None
+    # additive flags default to the reference's behaviour (square frame, one integration per pixel)
+    assert a["width"] is None and a["height"] is None and a["dedup"] is False
+    assert config.parse_args(["--dedup"]).dedup is True
 
 
 def test_scene_classes():
@@ -94,6 +95,36 @@ def test_run_manual_simulation_quirks_without_gpu(tmp_path, monkeypatch):
     assert img.shape == (6, 8, 3) and img.dtype == np.uint8 and not img.any()
     with pytest.raises(RuntimeError):
         run_manual_simulation(bh, ob, steps=10, delta=0.1, use_cuda=False, boundary_radius=31, n_samples=2)
+
+
+def test_dedup_flag_reaches_the_render_call(tmp_path, monkeypatch):
+    """`main.py --dedup` -> run_manual_simulation(dedup=True) -> render_frame(dedup=True) -> Handle.render(dedup=True)
+    (plumbing only: the library call is intercepted, there is no GPU here)."""
+    import schw_b200
+    from schw_b200 import multigpu
+    from simulation.blackhole import BlackHole, Observer
+    from simulation.raytracing import run_manual_simulation
+    monkeypatch.chdir(tmp_path)
+    seen = {}
+
+    class Stop(Exception):
+        pass
+
+    class FakeHandle:
+        def initial_conditions_px(self, obs, pixels, mass):
+            return np.array([[0.0, 30.0, np.pi / 2, 0.0]]), np.zeros((1, 9))
+
+        def render(self, scene, tex, rb, re, rs, extras=False, dedup=False):
+            seen.update(extras=extras, dedup=dedup, rows=(rb, re, rs), shape=(scene.height, scene.width))
+            raise Stop()
+
+    monkeypatch.setattr(schw_b200.native, "default_handle", lambda device=-1: FakeHandle())
+    bh = BlackHole(1.0); ob = Observer(np.array([30, 0, 0]), np.radians(80), (6, 8))
+    for flag in (True, False):
+        with pytest.raises(Stop):
+            run_manual_simulation(bh, ob, steps=10, delta=0.1, use_cuda=True, boundary_radius=31, n_samples=2, dedup=flag)
+        assert seen == dict(extras=True, dedup=flag, rows=(0, 6, 1), shape=(6, 8))
+    assert multigpu.render_frame.__defaults__[-1] is False          # opt-in
 
 
 def test_pinned_frame_buffers_are_plain_arrays_and_recycled(monkeypatch):
