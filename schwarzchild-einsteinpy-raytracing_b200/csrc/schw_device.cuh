@@ -466,7 +466,13 @@ __device__ __forceinline__ double pymod(double a, double b)
 //   get_initial_conditions  utils.py:91-141;  angles_to_p_sph :148-194;
 //   build_null_4momentum_ep_sph :39-88 (future=True)
 // ---------------------------------------------------------------------------------------------
+// error bits raised by the device code and reported by the host entry points (Counters::err in schw_kernels.cu)
+constexpr unsigned kErrTexWait  = 1u;   // the texture-ready flag never arrived (wait_flag_warp timed out)
+constexpr unsigned kErrRayPlane = 2u;   // utils.py:113,126: the rotated ray does not lie in the equatorial plane
+constexpr unsigned kErrNullCond = 4u;   // utils.py:80-81: negative discriminant of the null condition
+
 struct RayIC {
+    unsigned err;      // kErr* bits of this ray (0 for every finite camera ray)
     double p0[4];
     double alpha;      // camera angle pi - h_phi: p0 is a function of it alone (key of the geodesic de-duplication)
     double alpha0, beta;
@@ -483,6 +489,11 @@ __device__ __forceinline__ void initial_conditions_px(const SceneParams &sc, dou
     sincos(-beta, &s, &c);
     const double rx = d0;
     const double ry = c * d1 - s * d2;
+    // utils.py:113 `assert abs(ray_xy[2]) < 1e-6` and :126 `assert abs(h_theta - pi/2) < 1e-6`: for a unit vector the
+    // second (|atan2(rz, hypot(rx, ry))| < 1e-6) holds whenever the first does, up to the last digit of the 1e-6; both
+    // fail on NaN (pixel == observer).  Reported as SCHW_E_RAYPLANE by the host entry points.
+    const double rz = s * d1 + c * d2;
+    ic.err = (fabs(rz) < 1e-6) ? 0u : kErrRayPlane;
     // h_phi = atan2(y', x') of the rotated ray (cartesian_to_spherical_fast, utils.py:124)
     const double h_phi = atan2(ry, rx);
     const double alpha = 3.141592653589793 - h_phi;
@@ -493,6 +504,7 @@ __device__ __forceinline__ void initial_conditions_px(const SceneParams &sc, dou
     const double pph = sa * sc.r_obs;
     const double C = sc.grr * pr * pr + sc.gthth * pth * pth + sc.gphph * pph * pph;
     const double disc = sc.m4A * C;
+    if (disc < 0.0) ic.err |= kErrNullCond;      // utils.py:80-81 (unreachable for f > 0; NaN passes, as in the reference)
     ic.p0[0] = sqrt(disc) / sc.twomA;
     ic.p0[1] = pr; ic.p0[2] = pth; ic.p0[3] = pph;
     ic.alpha = alpha;
