@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SCHW_ABI_VERSION 1
+#define SCHW_ABI_VERSION 2
 
 /* error codes */
 #define SCHW_OK            0
@@ -36,6 +36,10 @@ extern "C" {
 #define SCHW_E_HORIZON    -3   /* observer inside the horizon: reference raises ValueError   (simulation/utils.py:67-68)  */
 #define SCHW_E_NULLCOND   -4   /* negative discriminant:        reference raises RuntimeError (simulation/utils.py:80-81)  */
 #define SCHW_E_RAYPLANE   -5   /* ray not in the equatorial plane after rotation: AssertionError (simulation/utils.py:113,126) */
+/* The last two are detected per ray ON THE DEVICE (a sticky error word, read back before a host-pointer entry point
+ * returns; the outputs are then undefined, as after the reference's exception).  Enqueue-only `_dev` entry points
+ * cannot report them at call time: schw_last_status() does, after the work has finished.  The same word carries a
+ * texture upload that never arrived (see schw_set_tex_ready_flag), reported as SCHW_E_CUDA. */
 #define SCHW_E_NOMEM      -6
 
 /* ray classes, in the order of the reference's `collision` strings (simulation/raytracing.py:210-272) */
@@ -129,6 +133,10 @@ int  schw_integrate_batch_rows(schw_handle *h, const double *q0s, const double *
 int  schw_initial_conditions(schw_handle *h, const schw_scene *scene, int row_begin, int row_end,
                              int row_stride, double *q0s, double *ic);
 
+/* q0 = (0, r_obs, theta_obs, phi_obs), the initial position shared by every camera ray of the scene (simulation/utils.py:
+ * 118,140: cartesian_to_spherical_fast of the observer); host arithmetic, needs no device. */
+int  schw_observer_q0(const schw_scene *scene, double *q0);
+
 /* Same for caller-supplied pixel positions: get_initial_conditions(observer_pos, pixel_pos, mass_bh=)
  * (simulation/utils.py:91-141) as called per ray by the reference's scripts.  obs: (3,), pixels: (n,3). */
 int  schw_initial_conditions_px(schw_handle *h, const double *obs, const double *pixels, int64_t n,
@@ -155,6 +163,16 @@ int  schw_render_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_t
                      int row_begin, int row_end, int row_stride,
                      uint8_t *d_rgb, uint8_t *d_cls, const schw_ray_outputs *d_extra,
                      void *cuda_stream);
+/* Same with explicit row pitches (bytes between consecutive visited rows; 0 = packed: 3*width and width), so the kernel can
+ * write straight into a caller-defined block -- e.g. rgb and class side by side in the (rows, 4*width) u8 message of the
+ * multi-GPU gather: d_cls = d_rgb + 3*width, both pitches 4*width. */
+int  schw_render_dev_pitched(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex,
+                             int row_begin, int row_end, int row_stride,
+                             uint8_t *d_rgb, int64_t rgb_row_pitch, uint8_t *d_cls, int64_t cls_row_pitch,
+                             const schw_ray_outputs *d_extra, void *cuda_stream);
+/* Waits for the last call on this handle and returns SCHW_OK or the error its device code flagged (SCHW_E_RAYPLANE,
+ * SCHW_E_NULLCOND, SCHW_E_CUDA for a texture that never arrived).  Host-pointer entry points check this themselves. */
+int  schw_last_status(schw_handle *h);
 /* ---- next rows (opt-in): geodesic de-duplication -------------------------------
  * Same arguments, same outputs -- bit for bit -- as schw_render / schw_render_dev.  Every camera ray of the reference
  * starts at the same q0 with a 4-momentum that depends only on its angle alpha to the optical axis (simulation/utils.py:
@@ -172,6 +190,24 @@ int  schw_render_dedup_dev(schw_handle *h, const schw_scene *scene, const uint8_
                            uint8_t *d_rgb, uint8_t *d_cls, const schw_ray_outputs *d_extra,
                            void *cuda_stream);
 int  schw_last_dedup_stats(schw_handle *h, uint64_t *unique_rays, uint64_t *pixel_steps);
+/* The same pipeline stage by stage, for the ranks of a multi-GPU job that SHARE the integration of the distinct rays
+ * (schw_b200/multigpu.py; the reference integrates every pixel in one process, simulation/raytracing.py:98-120):
+ *   plan       every rank: keys of the WHOLE frame -> sort -> distinct rays (identical on all ranks; synchronises the
+ *              stream once).  Distinct ray u (in order of camera angle) gets slot (u % world)*chunk + u / world,
+ *              chunk = ceil(n_unique / world): rank r owns slots [r*chunk, r*chunk + count_r) = every world-th ray.
+ *   integrate  rank r integrates its slots into d_fq_all (world*chunk, 4) f64 / d_ns_all (world*chunk) i32.
+ *              -- the caller all-gathers the two arrays (chunk rows per rank) --
+ *   epilogue   every rank: rotate back, classify, texel lookup for its own rows from the gathered final states;
+ *              outputs and pitches as schw_render_dev_pitched. */
+int  schw_dedup_plan_dev(schw_handle *h, const schw_scene *scene, int world, uint64_t *n_unique, uint64_t *chunk,
+                         void *cuda_stream);
+int  schw_dedup_integrate_dev(schw_handle *h, const schw_scene *scene, int rank, double *d_fq_all, int32_t *d_ns_all,
+                              void *cuda_stream);
+int  schw_dedup_epilogue_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex,
+                             int row_begin, int row_end, int row_stride,
+                             uint8_t *d_rgb, int64_t rgb_row_pitch, uint8_t *d_cls, int64_t cls_row_pitch,
+                             const schw_ray_outputs *d_extra, const double *d_fq_all, const int32_t *d_ns_all,
+                             void *cuda_stream);
 
 /* Overlap of the texture upload with the start of a frame (optional, one-shot): the next schw_render_dev call on this
  * handle may be enqueued BEFORE its texture has arrived in d_tex; the kernel waits -- per ray, only at the texel lookup
@@ -192,6 +228,16 @@ int  schw_last_counters(schw_handle *h, uint64_t *total_steps, uint64_t *warp_it
  * 99-132): ray-sphere intersection at boundary radius r_max, truncating texel map.
  * Uses scene->obs, fov, height, width, r_max, patch_*, flip_*.  rgb: (height,width,3) u8. */
 int  schw_flat_render(schw_handle *h, const schw_scene *scene, const uint8_t *tex, uint8_t *rgb);
+/* Replaces cuda_flat_raytrace and cuda_flat_raytrace_with_trajectories (simulation/cuda_geodesic.py:214-292, kernels
+ * :18-208; imported by simulation/background.py:77,95): caller-supplied unit ray directions (n,3) from obs (3,),
+ * bg (tex_h,tex_w,3) u8, out_rgb (n,3) u8.  With n_sampled > 0 also the n_points equally spaced points from the observer
+ * to the hit point of every ray listed in sampled_indices (flat ray numbers): out_trajs (n_sampled,n_points,3) f64, zero
+ * rows for rays that miss the boundary sphere. */
+int  schw_flat_raytrace(schw_handle *h, const double *obs, const double *ray_dirs, int64_t n, double boundary_radius,
+                        double patch_center_theta, double patch_center_phi, double patch_size_theta,
+                        double patch_size_phi, int flip_theta, int flip_phi, const uint8_t *bg, int tex_h, int tex_w,
+                        uint8_t *out_rgb, const int32_t *sampled_indices, int64_t n_sampled, int64_t n_points,
+                        double *out_trajs);
 
 /* ---- measurement helper ------------------------------------------------------------------------
  * Register-resident DFMA chains on every SM: measured FP64 FMA peak of the device in TFLOP/s

@@ -53,7 +53,7 @@ struct Counters {
     unsigned long long warp_iters;   // loop bodies executed, summed over warps (32 x this = lane-steps issued)
     unsigned long long planar_iters; // of those, completed entirely on the planar fast path
     int batch_planar;                // verdict of batch_probe_kernel
-    int _pad;
+    unsigned err;                    // kErr* bits raised by the device code of this call (schw_device.cuh)
     unsigned long long pixel_steps;  // de-duplicated render: steps summed over PIXELS (what one ray per pixel would take)
 };
 
@@ -73,6 +73,7 @@ struct BatchJob {
 
     __device__ __forceinline__ bool skip() const { return select && *select != want; }
     __device__ __forceinline__ const unsigned *ready_flag() const { return nullptr; }
+    __device__ __forceinline__ unsigned *err_word() const { return nullptr; }
     __device__ __forceinline__ bool ends_at_once(const StepParams &) const { return false; }
     __device__ __forceinline__ long long queue_len() const { return n; }
     __device__ __forceinline__ long long resolve(long long q) const { return q; }
@@ -99,14 +100,18 @@ struct BatchJob {
     }
 };
 
-// Warp-uniform bounded spin (about 2 s, then give up and read whatever is there) until the word at `flag` is non-zero.
-// The flag is written by a copy-engine memcpy that is stream-ordered after the texture upload, so a frame's integration
-// starts while its texture is still crossing PCIe; the first rays end milliseconds later, normally long after the flag.
+// Warp-uniform bounded spin (about 2 s) until the word at `flag` is non-zero.  The flag is written by a copy-engine
+// memcpy that is stream-ordered after the texture upload, so a frame's integration starts while its texture is still
+// crossing PCIe; the first rays end milliseconds later, normally long after the flag.  If the flag never arrives
+// (a stalled pageable upload, a time-sliced GPU) the texels that follow may be stale: kErrTexWait is raised in *err and
+// every host entry point / schw_last_status turns it into SCHW_E_CUDA -- never a silently wrong frame.
 // The exit test is a vote, so the loop is convergent by construction (call from convergent code only).
-__device__ __forceinline__ void wait_flag_warp(const unsigned *flag)
+__device__ __forceinline__ void wait_flag_warp(const unsigned *flag, unsigned *err)
 {
     const volatile unsigned *f = flag;
-    for (int spin = 0; spin < (1 << 22) && !__any_sync(0xffffffffu, *f != 0u); ++spin) __nanosleep(512);
+    bool seen = false;
+    for (int spin = 0; spin < (1 << 22) && !(seen = __any_sync(0xffffffffu, *f != 0u)); ++spin) __nanosleep(512);
+    if (!seen && (threadIdx.x & 31u) == 0u) atomicOr(err, kErrTexWait);
     __threadfence();
 }
 
@@ -114,8 +119,11 @@ struct RenderJob {
     SceneParams sc;
     const uint8_t *__restrict__ tex;
     const unsigned *tex_ready;          // NULL, or the flag that says the texture upload has landed (see wait_flag)
+    unsigned *err;                      // Counters::err of the call
     uint8_t *__restrict__ rgb;
     uint8_t *__restrict__ cls;
+    long long rgb_pitch, cls_pitch;     // bytes between visited rows (3w and w when packed; 4w for both inside a (rows, 4w)
+                                        // rgb ++ cls gather block, see schw_render_dev_pitched)
     double *__restrict__ final_q;
     double *__restrict__ ic;
     double *__restrict__ hit;
@@ -132,6 +140,7 @@ struct RenderJob {
     __device__ __forceinline__ bool skip() const { return false; }
     // the flag a warp must see before its first epilogue (texel lookup), or NULL
     __device__ __forceinline__ const unsigned *ready_flag() const { return tex_ready; }
+    __device__ __forceinline__ unsigned *err_word() const { return err; }
     // every ray of the frame starts at r_obs: do the rays end before their first step (cuda_geodesic.py:598)?
     __device__ __forceinline__ bool ends_at_once(const StepParams &P) const { return P.steps <= 0 || terminated(sc.r_obs, P); }
     __device__ __forceinline__ long long queue_len() const { return qlen; }
@@ -153,6 +162,7 @@ struct RenderJob {
         st[0] = make_double2(0.0, sc.r_obs); st[kBlock] = make_double2(sc.th_obs, sc.ph_obs);
         st[2 * kBlock] = make_double2(r.p0[0], r.p0[1]); st[3 * kBlock] = make_double2(r.p0[2], r.p0[3]);
         slot = make_double2(r.alpha0, r.beta);
+        if (r.err) atomicOr(err, r.err);
         if (ic) {
             double *o = ic + 9 * k;
             o[0] = r.p0[0]; o[1] = r.p0[1]; o[2] = r.p0[2]; o[3] = r.p0[3];
@@ -173,9 +183,10 @@ struct RenderJob {
         const double th = nan_exit ? nanv : th_, ph = nan_exit ? nanv : ph_;
         RayHit o;
         classify(sc, tex, r, th, ph, slot.x, slot.y, o);
-        uint8_t *c3 = rgb + 3 * k;
+        const int row = (int)(k / sc.width), j = (int)(k - (long long)row * sc.width);
+        uint8_t *c3 = rgb + row * rgb_pitch + 3 * j;
         c3[0] = o.r; c3[1] = o.g; c3[2] = o.b;
-        cls[k] = o.cls;
+        cls[row * cls_pitch + j] = o.cls;
         if (final_q) {
             double2 *q = reinterpret_cast<double2 *>(final_q + 4 * k);
             q[0] = make_double2(t, r); q[1] = make_double2(th, ph);
@@ -243,7 +254,7 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     while (true) {
         // ---- service (divergent, so batched): epilogue of the finished rays, then refill ----
         if (!inputs_ready && (job.ends_at_once(P) || __any_sync(kFull, waiting))) {
-            wait_flag_warp(job.ready_flag());                      // the first epilogue of this warp: its texel lookup
+            wait_flag_warp(job.ready_flag(), job.err_word());                      // the first epilogue of this warp: its texel lookup
             inputs_ready = true;
         }
         if (waiting) {
@@ -487,15 +498,19 @@ __global__ void dedup_heads_kernel(const unsigned long long *__restrict__ keys_s
     head[i] = (i == 0 || keys_sorted[i] != keys_sorted[i - 1]) ? 1 : 0;
 }
 
-// uid1[i] = inclusive sum of head[] = 1-based index of the distinct ray of sorted position i
+// uid1[i] = inclusive sum of head[] = 1-based index (in order of alpha) of the distinct ray of sorted position i.
+// Distinct ray u lives in SLOT (u % world) * chunk + u / world: with `world` ranks sharing the integration, rank r owns the
+// contiguous slots [r*chunk, r*chunk + count_r) and every world-th distinct ray in alpha order -- neighbouring alphas cost
+// the same, so the shares are balanced; world = 1 gives slot = u.
 __global__ void dedup_scatter_kernel(const __grid_constant__ SceneParams sc, long long n, const unsigned *__restrict__ pix_sorted,
                                      const int *__restrict__ head, const int *__restrict__ uid1, int *__restrict__ ray_of_pixel,
-                                     double *__restrict__ uq0, double *__restrict__ up0)
+                                     double *__restrict__ uq0, double *__restrict__ up0, int world, int chunk)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned k = pix_sorted[i];
-    const int u = uid1[i] - 1;
+    const int u0 = uid1[i] - 1;
+    const int u = (u0 % world) * chunk + u0 / world;
     ray_of_pixel[k] = u;
     if (head[i]) {
         const int row = (int)(k / sc.width), j = (int)(k - (long long)row * sc.width);
@@ -509,7 +524,7 @@ __global__ void dedup_scatter_kernel(const __grid_constant__ SceneParams sc, lon
 
 // per pixel: its own (alpha0, beta) again, the final state of its geodesic, then the same epilogue as the fused kernel
 __global__ void __launch_bounds__(kBlock)
-dedup_epilogue_kernel(const __grid_constant__ RenderJob job, const int *__restrict__ ray_of_pixel,
+dedup_epilogue_kernel(const __grid_constant__ RenderJob job, const int *__restrict__ ray_of_pixel, int plan_rb, int plan_rs,
                       const double *__restrict__ ufq, const int32_t *__restrict__ unsteps, Counters *ctr)
 {
     __shared__ double2 s_stage[4 * kBlock];
@@ -520,7 +535,11 @@ dedup_epilogue_kernel(const __grid_constant__ RenderJob job, const int *__restri
     if (k < job.n) {
         double2 slot;
         job.load(k, &s_stage[threadIdx.x], slot);           // writes ic[k] if requested; slot = (alpha0, beta)
-        const int u = ray_of_pixel[k];
+        // the plan may cover more rows than this call renders (multi-GPU: the whole frame): packed ray k of this call is
+        // pixel (row_begin + row*row_stride, j) = packed pixel ((i - plan_rb) / plan_rs, j) of the plan
+        const int row = (int)(k / job.sc.width), j = (int)(k - (long long)row * job.sc.width);
+        const long long kp = (long long)((job.sc.row_begin + row * job.sc.row_stride - plan_rb) / plan_rs) * job.sc.width + j;
+        const int u = ray_of_pixel[kp];
         const double2 a = *reinterpret_cast<const double2 *>(ufq + 4 * (size_t)u);
         const double2 b = *reinterpret_cast<const double2 *>(ufq + 4 * (size_t)u + 2);
         const int ns = unsteps[u];
@@ -535,13 +554,14 @@ dedup_epilogue_kernel(const __grid_constant__ RenderJob job, const int *__restri
 // Stage kernels (boundary / parity testing): one thread per ray, static mapping.
 // ---------------------------------------------------------------------------------------------
 __global__ void ic_kernel(const __grid_constant__ SceneParams sc, long long n, double *__restrict__ q0s,
-                          double *__restrict__ ic)
+                          double *__restrict__ ic, unsigned *err)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int row = (int)(k / sc.width), j = (int)(k - (long long)row * sc.width);
     RayIC r;
     initial_conditions(sc, sc.row_begin + row * sc.row_stride, j, r);
+    if (r.err) atomicOr(err, r.err);
     q0s[4 * k] = 0.0; q0s[4 * k + 1] = sc.r_obs; q0s[4 * k + 2] = sc.th_obs; q0s[4 * k + 3] = sc.ph_obs;
     double *o = ic + 9 * k;
     o[0] = r.p0[0]; o[1] = r.p0[1]; o[2] = r.p0[2]; o[3] = r.p0[3];
@@ -550,12 +570,13 @@ __global__ void ic_kernel(const __grid_constant__ SceneParams sc, long long n, d
 }
 
 __global__ void ic_px_kernel(const __grid_constant__ SceneParams sc, const double *__restrict__ pixels, long long n,
-                             double *__restrict__ q0s, double *__restrict__ ic)
+                             double *__restrict__ q0s, double *__restrict__ ic, unsigned *err)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     RayIC r;
     initial_conditions_px(sc, pixels[3 * k], pixels[3 * k + 1], pixels[3 * k + 2], r);
+    if (r.err) atomicOr(err, r.err);
     q0s[4 * k] = 0.0; q0s[4 * k + 1] = sc.r_obs; q0s[4 * k + 2] = sc.th_obs; q0s[4 * k + 3] = sc.ph_obs;
     double *o = ic + 9 * k;
     o[0] = r.p0[0]; o[1] = r.p0[1]; o[2] = r.p0[2]; o[3] = r.p0[3];
@@ -592,6 +613,42 @@ struct FlatParams {
     int32_t height, width, flip_theta, flip_phi;
 };
 
+// Shared by both flat kernels: unit direction d from the observer -> hit on the boundary sphere -> patch test ->
+// truncating texel map (background.py:106-132; the same arithmetic as the reference's Numba variant,
+// cuda_geodesic.py:45-113).  Returns false (black pixel) when the ray misses the sphere; hit[] receives the hit point.
+__device__ __forceinline__ bool flat_shade(const FlatParams &fp, const double d[3], const uint8_t *__restrict__ tex,
+                                           uint8_t &r8, uint8_t &g8, uint8_t &b8, double hit[3])
+{
+    r8 = g8 = b8 = 0;
+    const double a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    const double b = 2 * (fp.obs[0] * d[0] + fp.obs[1] * d[1] + fp.obs[2] * d[2]);
+    const double c = fp.obs_dot_obs - fp.r2;
+    const double disc = b * b - 4 * a * c;
+    if (disc < 0) return false;
+    const double t = (-b + sqrt(disc)) / (2 * a);
+    const double hx = fp.obs[0] + t * d[0], hy = fp.obs[1] + t * d[1], hz = fp.obs[2] + t * d[2];
+    hit[0] = hx; hit[1] = hy; hit[2] = hz;
+    const double r = sqrt(hx * hx + hy * hy + hz * hz);
+    const double theta = acos(hz / r);
+    const double phi = atan2(hy, hx);
+    const double two_pi = 6.283185307179586;
+    // _in_phi_patch, background.py:8-17
+    const double pm = pymod(phi, two_pi);
+    const bool in_phi = (fp.phi0m <= fp.phi1m) ? (fp.phi0m <= pm && pm <= fp.phi1m) : (pm >= fp.phi0m || pm <= fp.phi1m);
+    if (theta >= fp.theta0 && theta <= fp.theta1 && in_phi) {
+        const double theta_map = fp.flip_theta ? (3.141592653589793 - theta) : theta;
+        const double phi_map = fp.flip_phi ? -phi : phi;
+        long long ub = (long long)((theta_map - fp.theta0) / (fp.theta1 - fp.theta0) * (fp.height - 1));
+        const double phi_mod = pymod(phi_map - fp.phi0, two_pi);
+        long long vb = (long long)(phi_mod / fp.phi_span * (fp.width - 1));
+        ub = ub < 0 ? 0 : (ub > fp.height - 1 ? fp.height - 1 : ub);
+        vb = vb < 0 ? 0 : (vb > fp.width - 1 ? fp.width - 1 : vb);
+        const uint8_t *tx = tex + ((size_t)ub * fp.width + vb) * 3;
+        r8 = __ldg(tx); g8 = __ldg(tx + 1); b8 = __ldg(tx + 2);
+    }
+    return true;
+}
+
 __global__ void flat_kernel(const __grid_constant__ FlatParams fp, const uint8_t *__restrict__ tex,
                             uint8_t *__restrict__ rgb)
 {
@@ -601,42 +658,54 @@ __global__ void flat_kernel(const __grid_constant__ FlatParams fp, const uint8_t
     const int i = (int)(k / fp.width), j = (int)(k - (long long)i * fp.width);
     const double u = (j + 0.5) / fp.width - 0.5;
     const double v = (i + 0.5) / fp.height - 0.5;
-    double d[3], nrm2 = 0.0;
+    double d[3], hit[3];
     for (int a = 0; a < 3; ++a) {
         const double px = (fp.pc[a] + (u * fp.plane_width) * fp.right[a]) + (v * fp.plane_height) * fp.up[a];
         d[a] = px - fp.obs[a];
     }
-    nrm2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-    const double nrm = sqrt(nrm2);
+    const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     d[0] /= nrm; d[1] /= nrm; d[2] /= nrm;
-    const double a = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-    const double b = 2 * (fp.obs[0] * d[0] + fp.obs[1] * d[1] + fp.obs[2] * d[2]);
-    const double c = fp.obs_dot_obs - fp.r2;
-    const double disc = b * b - 4 * a * c;
-    uint8_t r8 = 0, g8 = 0, b8 = 0;
-    if (!(disc < 0)) {
-        const double t = (-b + sqrt(disc)) / (2 * a);
-        const double hx = fp.obs[0] + t * d[0], hy = fp.obs[1] + t * d[1], hz = fp.obs[2] + t * d[2];
-        const double r = sqrt(hx * hx + hy * hy + hz * hz);
-        const double theta = acos(hz / r);
-        const double phi = atan2(hy, hx);
-        const double two_pi = 6.283185307179586;
-        // _in_phi_patch, background.py:8-17
-        const double pm = pymod(phi, two_pi);
-        const bool in_phi = (fp.phi0m <= fp.phi1m) ? (fp.phi0m <= pm && pm <= fp.phi1m) : (pm >= fp.phi0m || pm <= fp.phi1m);
-        if (theta >= fp.theta0 && theta <= fp.theta1 && in_phi) {
-            const double theta_map = fp.flip_theta ? (3.141592653589793 - theta) : theta;
-            const double phi_map = fp.flip_phi ? -phi : phi;
-            long long ub = (long long)((theta_map - fp.theta0) / (fp.theta1 - fp.theta0) * (fp.height - 1));
-            const double phi_mod = pymod(phi_map - fp.phi0, two_pi);
-            long long vb = (long long)(phi_mod / fp.phi_span * (fp.width - 1));
-            ub = ub < 0 ? 0 : (ub > fp.height - 1 ? fp.height - 1 : ub);
-            vb = vb < 0 ? 0 : (vb > fp.width - 1 ? fp.width - 1 : vb);
-            const uint8_t *tx = tex + ((size_t)ub * fp.width + vb) * 3;
-            r8 = __ldg(tx); g8 = __ldg(tx + 1); b8 = __ldg(tx + 2);
-        }
-    }
+    uint8_t r8, g8, b8;
+    flat_shade(fp, d, tex, r8, g8, b8, hit);
     rgb[3 * k] = r8; rgb[3 * k + 1] = g8; rgb[3 * k + 2] = b8;
+}
+
+// cuda_flat_raytrace (cuda_geodesic.py:214-250, kernel :18-113): caller-supplied unit directions, one ray per thread;
+// fp.height / fp.width are the TEXTURE's dimensions (the reference reads them from bg_array.shape, :223).
+__global__ void flat_dirs_kernel(const __grid_constant__ FlatParams fp, const double *__restrict__ dirs, long long n,
+                                 const uint8_t *__restrict__ tex, uint8_t *__restrict__ rgb)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double d[3] = {dirs[3 * k], dirs[3 * k + 1], dirs[3 * k + 2]};
+    double hit[3];
+    uint8_t r8, g8, b8;
+    flat_shade(fp, d, tex, r8, g8, b8, hit);
+    rgb[3 * k] = r8; rgb[3 * k + 1] = g8; rgb[3 * k + 2] = b8;
+}
+
+// The trajectory half of cuda_flat_raytrace_with_trajectories (kernel :150-163): n_points equally spaced points from the
+// observer to the hit point of ray sampled[s]; one thread per (s, point).  Rows of rays that miss the sphere stay zero.
+__global__ void flat_traj_kernel(const __grid_constant__ FlatParams fp, const double *__restrict__ dirs, long long n,
+                                 const int32_t *__restrict__ sampled, int n_sampled, int n_points, double *__restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_sampled * n_points) return;
+    const int s = (int)(t / n_points), p = (int)(t - (long long)s * n_points);
+    const long long k = sampled[s];
+    if (k < 0 || k >= n) return;
+    const double dx = dirs[3 * k], dy = dirs[3 * k + 1], dz = dirs[3 * k + 2];
+    const double a = dx * dx + dy * dy + dz * dz;
+    const double b = 2.0 * (fp.obs[0] * dx + fp.obs[1] * dy + fp.obs[2] * dz);
+    const double disc = b * b - 4.0 * a * (fp.obs_dot_obs - fp.r2);
+    if (disc < 0.0) return;
+    const double tt = (-b + sqrt(disc)) / (2.0 * a);
+    const double hx = fp.obs[0] + tt * dx, hy = fp.obs[1] + tt * dy, hz = fp.obs[2] + tt * dz;
+    const double alpha = p / (n_points - 1.0);
+    double *o = out + 3 * t;
+    o[0] = fp.obs[0] + alpha * (hx - fp.obs[0]);
+    o[1] = fp.obs[1] + alpha * (hy - fp.obs[1]);
+    o[2] = fp.obs[2] + alpha * (hz - fp.obs[2]);
 }
 
 // Device math primitives of the flow, exposed for accuracy tests (tests/test_gpu_math.py).
@@ -710,7 +779,8 @@ struct schw_handle {
     cudaEvent_t ev_copy0 = nullptr, ev_copy1 = nullptr;
     cudaEvent_t ev_dd = nullptr;          // the cached geodesics of the de-duplicated render are complete
     unsigned *tex_flag = nullptr;         // device word: "texture of the current frame has landed"
-    unsigned *one_pinned = nullptr;       // page-locked 1, the source of the copy that raises tex_flag
+    unsigned *one_pinned = nullptr;       // page-locked {1, err}: [0] the source of the copy that raises tex_flag,
+                                          // [1] receives Counters::err at the end of a host-pointer call
     const unsigned *next_tex_ready = nullptr;   // one-shot flag for the next schw_render_dev (schw_set_tex_ready_flag)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -722,7 +792,12 @@ struct schw_handle {
     DevBuf dd_keys, dd_keys2, dd_pix, dd_pix2, dd_head, dd_uid, dd_map, dd_tmp, dd_q0, dd_p0, dd_fq, dd_ns;   // de-duplication
     bool in_pipeline = false;             // a multi-kernel entry point owns the timing events and the counters
     long long last_unique = 0;            // distinct rays of the last de-duplicated render
-    bool dd_valid = false;                // dd_map / dd_fq / dd_ns hold the geodesics of the frame described by dd_key
+    bool dd_valid = false;                // dd_fq / dd_ns hold the geodesics of the frame described by dd_key
+    bool dd_plan_valid = false;           // dd_map / dd_q0 / dd_p0 hold the plan described by dd_plan_key
+    struct { double v[16]; } dd_plan_key = {{0}};
+    int dd_world = 1, dd_chunk = 0;       // slot layout of the plan: distinct ray u -> (u % world) * chunk + u / world
+    int dd_plan_rb = 0, dd_plan_rs = 1, dd_plan_rows = 0;   // rows the plan covers
+    cudaEvent_t ev_plan = nullptr;
     double dd_key[16] = {0};
     double order_key[12] = {0};   // camera geometry the cached tile order was built for
     long long order_tiles = 0;
@@ -743,6 +818,27 @@ static int ensure(DevBuf &b, size_t bytes)
         int rc_ = ensure(buf, bytes);                \
         if (rc_) return rc_;                         \
     } while (0)
+
+// The error bits the device code raised during a call (Counters::err), as the reference's exceptions:
+// AssertionError (utils.py:113,126) before RuntimeError (utils.py:80-81), in the order get_initial_conditions raises them.
+static int device_error_code(unsigned e)
+{
+    if (e & kErrRayPlane)
+        return fail(SCHW_E_RAYPLANE, "a ray does not lie in the equatorial plane after the rotation by -beta (|z'| >= 1e-6 or NaN: "
+                                     "pixel position equal to the observer position?)");
+    if (e & kErrNullCond) return fail(SCHW_E_NULLCOND, "Negative discriminant while enforcing null condition.");
+    if (e & kErrTexWait)
+        return fail(SCHW_E_CUDA, "the texture upload did not arrive within ~2 s of the first texel lookup (tex_ready flag never "
+                                 "raised); the frame is invalid");
+    return SCHW_OK;
+}
+// Last step of a host-pointer entry point: wait for the stream, then report what the device code flagged.
+static int sync_and_check(schw_handle *h, cudaStream_t st)
+{
+    CU(cudaMemcpyAsync(&h->one_pinned[1], &h->ctr->err, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return device_error_code(h->one_pinned[1]);
+}
 
 extern "C" int schw_abi_version(void) { return SCHW_ABI_VERSION; }
 extern "C" const char *schw_last_error(void) { return g_err.c_str(); }
@@ -775,9 +871,10 @@ extern "C" int schw_create(int device, schw_handle **out)
     CU(cudaEventCreateWithFlags(&h->ev_copy0, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_copy1, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_dd, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_plan, cudaEventDisableTiming));
     CU(cudaMalloc(&h->tex_flag, sizeof(unsigned)));
-    CU(cudaHostAlloc(&h->one_pinned, sizeof(unsigned), cudaHostAllocDefault));
-    *h->one_pinned = 1u;
+    CU(cudaHostAlloc(&h->one_pinned, 2 * sizeof(unsigned), cudaHostAllocDefault));
+    h->one_pinned[0] = 1u; h->one_pinned[1] = 0u;
     CU(cudaEventCreate(&h->ev0));
     CU(cudaEventCreate(&h->ev1));
     CU(cudaMalloc(&h->ctr, sizeof(Counters)));
@@ -802,6 +899,7 @@ extern "C" int schw_destroy(schw_handle *h)
     if (h->ev_copy0) cudaEventDestroy(h->ev_copy0);
     if (h->ev_copy1) cudaEventDestroy(h->ev_copy1);
     if (h->ev_dd) cudaEventDestroy(h->ev_dd);
+    if (h->ev_plan) cudaEventDestroy(h->ev_plan);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaStreamDestroy(h->stream);
@@ -860,6 +958,17 @@ extern "C" int schw_last_total_steps(schw_handle *h, uint64_t *total_steps)
     CU(cudaMemcpy(&c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost));
     *total_steps = c.total_steps;
     return SCHW_OK;
+}
+
+// For the enqueue-only (_dev) entry points: waits for the last call on this handle and returns what its device code flagged.
+extern "C" int schw_last_status(schw_handle *h)
+{
+    if (!h) return fail(SCHW_E_INVALID, "null handle");
+    CU(cudaSetDevice(h->device));
+    Counters c;
+    CU(cudaStreamSynchronize(h->last_stream ? h->last_stream : h->stream));
+    CU(cudaMemcpy(&c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost));
+    return device_error_code(c.err);
 }
 
 extern "C" int schw_last_counters(schw_handle *h, uint64_t *total_steps, uint64_t *warp_iters, uint64_t *planar_iters)
@@ -1000,6 +1109,17 @@ static int make_scene_params(const schw_scene *s, int row_begin, int row_end, in
     sc.has_texture = s->has_texture;
     sc.row_begin = row_begin; sc.row_stride = row_stride;
     sc.nrows = row_end > row_begin ? (row_end - row_begin + row_stride - 1) / row_stride : 0;
+    return SCHW_OK;
+}
+
+// q0 = (0, r_obs, theta_obs, phi_obs) of every camera ray of the scene (utils.py:118,140), host arithmetic only.
+extern "C" int schw_observer_q0(const schw_scene *scene, double *q0)
+{
+    if (!scene || !q0) return fail(SCHW_E_INVALID, "null argument");
+    SceneParams sc;
+    int rc = make_scene_params(scene, 0, scene->height, 1, sc);
+    if (rc) return rc;
+    q0[0] = 0.0; q0[1] = sc.r_obs; q0[2] = sc.th_obs; q0[3] = sc.ph_obs;
     return SCHW_OK;
 }
 
@@ -1229,15 +1349,15 @@ extern "C" int schw_initial_conditions(schw_handle *h, const schw_scene *scene, 
     if (n == 0) return SCHW_OK;
     ENSURE(h->fq, (size_t)n * 4 * sizeof(double));
     ENSURE(h->ic, (size_t)n * 9 * sizeof(double));
+    CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), h->stream));
     begin_timed(h, h->stream);
-    ic_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(sc, n, (double *)h->fq.p, (double *)h->ic.p);
+    ic_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(sc, n, (double *)h->fq.p, (double *)h->ic.p, &h->ctr->err);
     h->launches += 1;
     CU(cudaGetLastError());
     end_timed(h, h->stream);
     CU(cudaMemcpyAsync(q0s, h->fq.p, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(ic, h->ic.p, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    return SCHW_OK;
+    return sync_and_check(h, h->stream);
 }
 
 extern "C" int schw_initial_conditions_px(schw_handle *h, const double *obs, const double *pixels, int64_t n,
@@ -1257,16 +1377,16 @@ extern "C" int schw_initial_conditions_px(schw_handle *h, const double *obs, con
     cudaStream_t st = h->stream;
     ENSURE(h->in_a, (size_t)n * 24); ENSURE(h->fq, (size_t)n * 32); ENSURE(h->ic, (size_t)n * 72);
     CU(cudaMemcpyAsync(h->in_a.p, pixels, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
     begin_timed(h, st);
     ic_px_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sc, (const double *)h->in_a.p, (long long)n,
-                                                               (double *)h->fq.p, (double *)h->ic.p);
+                                                               (double *)h->fq.p, (double *)h->ic.p, &h->ctr->err);
     h->launches += 1;
     CU(cudaGetLastError());
     end_timed(h, st);
     CU(cudaMemcpyAsync(q0s, h->fq.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ic, h->ic.p, (size_t)n * 72, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    return SCHW_OK;
+    return sync_and_check(h, st);
 }
 
 // ---- stage 5 ------------------------------------------------------------------------------------
@@ -1374,15 +1494,20 @@ static int build_tile_order(schw_handle *h, const schw_scene *s, const ScenePara
 static bool lpt_order_enabled() { return env_switch_on("SCHW_LPT_ORDER"); }
 
 // ---- fused render -------------------------------------------------------------------------------
-extern "C" int schw_render_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex, int row_begin,
-                               int row_end, int row_stride, uint8_t *d_rgb, uint8_t *d_cls,
-                               const schw_ray_outputs *x, void *cuda_stream)
+extern "C" int schw_render_dev_pitched(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex, int row_begin,
+                                       int row_end, int row_stride, uint8_t *d_rgb, int64_t rgb_row_pitch,
+                                       uint8_t *d_cls, int64_t cls_row_pitch, const schw_ray_outputs *x, void *cuda_stream)
 {
     if (!h || !scene) return fail(SCHW_E_INVALID, "null argument");
     CU(cudaSetDevice(h->device));
     SceneParams sc;
     int rc = make_scene_params(scene, row_begin, row_end, row_stride, sc);
     if (rc) return rc;
+    if (rgb_row_pitch == 0) rgb_row_pitch = 3LL * sc.width;
+    if (cls_row_pitch == 0) cls_row_pitch = sc.width;
+    if (rgb_row_pitch < 3LL * sc.width || cls_row_pitch < sc.width) return fail(SCHW_E_INVALID, "row pitch smaller than a row");
+    if ((long long)sc.nrows * sc.width > 0x7fffffffLL)
+        return fail(SCHW_E_INVALID, "more than 2^31-1 rays in one call (the kernel indexes rays with 32-bit integers)");
     StepParams P;
     rc = make_step_params(scene->steps, scene->delta, 2.0 * scene->mass, scene->r_max, scene->omega, P);
     if (rc) return rc;
@@ -1395,6 +1520,7 @@ extern "C" int schw_render_dev(schw_handle *h, const schw_scene *scene, const ui
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     RenderJob job;
     job.sc = sc; job.tex = d_tex; job.rgb = d_rgb; job.cls = d_cls;
+    job.rgb_pitch = rgb_row_pitch; job.cls_pitch = cls_row_pitch; job.err = &h->ctr->err;
     job.tex_ready = scene->has_texture ? h->next_tex_ready : nullptr;
     h->next_tex_ready = nullptr;
     job.final_q = x ? x->final_q : nullptr;
@@ -1416,6 +1542,13 @@ extern "C" int schw_render_dev(schw_handle *h, const schw_scene *scene, const ui
     return rc;
 }
 
+extern "C" int schw_render_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex, int row_begin,
+                               int row_end, int row_stride, uint8_t *d_rgb, uint8_t *d_cls,
+                               const schw_ray_outputs *x, void *cuda_stream)
+{
+    return schw_render_dev_pitched(h, scene, d_tex, row_begin, row_end, row_stride, d_rgb, 0, d_cls, 0, x, cuda_stream);
+}
+
 extern "C" int schw_set_tex_ready_flag(schw_handle *h, const uint32_t *d_flag)
 {
     if (!h) return fail(SCHW_E_INVALID, "null handle");
@@ -1434,6 +1567,7 @@ extern "C" int schw_render(schw_handle *h, const schw_scene *scene, const uint8_
     CU(cudaSetDevice(h->device));
     const int nrows = row_end > row_begin ? (row_end - row_begin + row_stride - 1) / row_stride : 0;
     const size_t n = (size_t)nrows * scene->width;
+    if (n > 0x7fffffffULL) return fail(SCHW_E_INVALID, "more than 2^31-1 rays in one call (the kernel indexes rays with 32-bit integers)");
     if (n > 0 && (!rgb || !cls)) return fail(SCHW_E_INVALID, "null output");
     cudaStream_t st = h->stream;
     const size_t tb = (size_t)scene->height * scene->width * 3;
@@ -1472,14 +1606,132 @@ extern "C" int schw_render(schw_handle *h, const schw_scene *scene, const uint8_
         if (d.texel) CU(cudaMemcpyAsync(x->texel, d.texel, n * 8, cudaMemcpyDeviceToHost, st));
         if (d.nsteps) CU(cudaMemcpyAsync(x->nsteps, d.nsteps, n * 4, cudaMemcpyDeviceToHost, st));
     }
-    CU(cudaStreamSynchronize(st));
-    return SCHW_OK;
+    return sync_and_check(h, st);
 }
 
 // ---- de-duplicated render (N4, opt-in) ------------------------------------------------------------
 // Same contract and same output bits as schw_render_dev, but pixels whose camera angle agrees bitwise share one
-// integration (see dedup_key_kernel).  Unlike schw_render_dev it synchronises the stream once in the middle (the number
-// of distinct rays sizes the second half), so it is not enqueue-only.
+// integration (see dedup_key_kernel).  Three stages, also exported one by one so that the ranks of a multi-GPU job can
+// share the integration (schw_b200/multigpu.py): plan (keys -> sort -> distinct rays, ONE stream synchronisation: the
+// number of distinct rays sizes what follows), integrate (a rank's share of the distinct rays), epilogue (per pixel).
+struct DedupPlanKey { double v[16]; };
+static DedupPlanKey dedup_plan_key(const schw_scene *scene, int rb, int rs, int nrows, int world)
+{
+    DedupPlanKey k = {{scene->obs[0], scene->obs[1], scene->obs[2], scene->fov, (double)scene->height, (double)scene->width,
+                      (double)rb, (double)rs, (double)nrows, scene->mass, (double)world, 0.0, 0.0, 0.0, 0.0, 1.0}};
+    return k;
+}
+
+// Stage 1.  Rows (row_begin, row_end, row_stride) of the frame -> h->dd_map (slot of every packed pixel), h->dd_q0/p0
+// (initial conditions per slot), h->last_unique, h->dd_chunk.  Cached per camera geometry + rows + world.
+static int dedup_plan(schw_handle *h, const schw_scene *scene, int row_begin, int row_end, int row_stride, int world,
+                      cudaStream_t st)
+{
+    SceneParams sc;
+    int rc = make_scene_params(scene, row_begin, row_end, row_stride, sc);
+    if (rc) return rc;
+    if (world < 1) return fail(SCHW_E_INVALID, "world must be >= 1");
+    const long long n = (long long)sc.nrows * sc.width;
+    if (n > 0x7fffffffLL) return fail(SCHW_E_INVALID, "more than 2^31-1 rays");
+    const DedupPlanKey key = dedup_plan_key(scene, sc.row_begin, sc.row_stride, sc.nrows, world);
+    if (h->dd_plan_valid && memcmp(&key, &h->dd_plan_key, sizeof(key)) == 0) {
+        CU(cudaStreamWaitEvent(st, h->ev_plan, 0));
+        return SCHW_OK;
+    }
+    h->dd_plan_valid = false; h->dd_valid = false;
+    h->last_unique = 0; h->dd_chunk = 0; h->dd_world = world;
+    h->dd_plan_rb = sc.row_begin; h->dd_plan_rs = sc.row_stride; h->dd_plan_rows = sc.nrows;
+    if (n == 0) { memcpy(&h->dd_plan_key, &key, sizeof(key)); h->dd_plan_valid = true; CU(cudaEventRecord(h->ev_plan, st)); return SCHW_OK; }
+    ENSURE(h->dd_keys, (size_t)n * 8); ENSURE(h->dd_keys2, (size_t)n * 8);
+    ENSURE(h->dd_pix, (size_t)n * 4); ENSURE(h->dd_pix2, (size_t)n * 4);
+    ENSURE(h->dd_head, (size_t)n * 4); ENSURE(h->dd_uid, (size_t)n * 4); ENSURE(h->dd_map, (size_t)n * 4);
+    auto *keys = (unsigned long long *)h->dd_keys.p, *keys2 = (unsigned long long *)h->dd_keys2.p;
+    auto *pix = (unsigned *)h->dd_pix.p, *pix2 = (unsigned *)h->dd_pix2.p;
+    int *head = (int *)h->dd_head.p, *uid1 = (int *)h->dd_uid.p;
+    size_t tmp_sort = 0, tmp_scan = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys2, pix, pix2, (int)n, 0, 64, st));
+    CU(cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, head, uid1, (int)n, st));
+    ENSURE(h->dd_tmp, tmp_sort > tmp_scan ? tmp_sort : tmp_scan);
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    dedup_key_kernel<<<blocks, 256, 0, st>>>(sc, n, keys, pix);
+    CU(cudaGetLastError());
+    size_t tmp = h->dd_tmp.cap;
+    CU(cub::DeviceRadixSort::SortPairs(h->dd_tmp.p, tmp, keys, keys2, pix, pix2, (int)n, 0, 64, st));
+    dedup_heads_kernel<<<blocks, 256, 0, st>>>(keys2, n, head);
+    CU(cudaGetLastError());
+    tmp = h->dd_tmp.cap;
+    CU(cub::DeviceScan::InclusiveSum(h->dd_tmp.p, tmp, head, uid1, (int)n, st));
+    int n_unique = 0;
+    CU(cudaMemcpyAsync(&n_unique, uid1 + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));          // (the cub sort/scan are library calls on an opt-in path; this is its one host sync)
+    if (n_unique <= 0 || n_unique > n) return fail(SCHW_E_CUDA, "de-duplication produced an impossible ray count");
+    const int chunk = (n_unique + world - 1) / world;
+    ENSURE(h->dd_q0, (size_t)chunk * world * 32); ENSURE(h->dd_p0, (size_t)chunk * world * 32);
+    dedup_scatter_kernel<<<blocks, 256, 0, st>>>(sc, n, pix2, head, uid1, (int *)h->dd_map.p, (double *)h->dd_q0.p,
+                                                  (double *)h->dd_p0.p, world, chunk);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev_plan, st));
+    h->launches += 5;                                   // key, sort, heads, scan, scatter
+    h->last_unique = n_unique; h->dd_chunk = chunk;
+    memcpy(&h->dd_plan_key, &key, sizeof(key));
+    h->dd_plan_valid = true;
+    return SCHW_OK;
+}
+
+// Stage 2.  Rank `rank`'s share of the distinct rays of the current plan: slots [rank*chunk, rank*chunk + count) of
+// d_fq_all (world*chunk, 4) / d_ns_all (world*chunk).
+static int dedup_integrate(schw_handle *h, const schw_scene *scene, int rank, double *d_fq_all, int32_t *d_ns_all, cudaStream_t st)
+{
+    if (!h->dd_plan_valid) return fail(SCHW_E_INVALID, "no de-duplication plan on this handle");
+    const int world = h->dd_world, chunk = h->dd_chunk;
+    if (rank < 0 || rank >= world) return fail(SCHW_E_INVALID, "rank out of range");
+    const long long U = h->last_unique;
+    const long long count = U > rank ? (U - rank + world - 1) / world : 0;       // distinct rays u = rank (mod world)
+    const size_t first = (size_t)rank * chunk;
+    return integrate_batch_impl(h, (const double *)h->dd_q0.p + 4 * first, (const double *)h->dd_p0.p + 4 * first, count,
+                                scene->steps, scene->delta, 2.0 * scene->mass, scene->r_max, scene->omega,
+                                d_fq_all + 4 * first, d_ns_all + first, st);
+}
+
+// Stage 3.  Per-pixel epilogue of the rows of THIS call (a subset of the plan's rows) from the distinct rays' final states.
+static int dedup_epilogue(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex, int row_begin, int row_end,
+                          int row_stride, uint8_t *d_rgb, long long rgb_pitch, uint8_t *d_cls, long long cls_pitch,
+                          const schw_ray_outputs *x, const double *d_fq_all, const int32_t *d_ns_all, cudaStream_t st)
+{
+    if (!h->dd_plan_valid) return fail(SCHW_E_INVALID, "no de-duplication plan on this handle");
+    SceneParams sc;
+    int rc = make_scene_params(scene, row_begin, row_end, row_stride, sc);
+    if (rc) return rc;
+    const long long n = (long long)sc.nrows * sc.width;
+    if (n == 0) return SCHW_OK;
+    if (scene->has_texture && !d_tex) return fail(SCHW_E_INVALID, "has_texture set but tex is NULL");
+    if (!d_rgb || !d_cls) return fail(SCHW_E_INVALID, "null output");
+    const int prb = h->dd_plan_rb, prs = h->dd_plan_rs;
+    const int last = sc.row_begin + (sc.nrows - 1) * sc.row_stride;
+    if ((sc.row_begin - prb) % prs != 0 || (sc.nrows > 1 && sc.row_stride % prs != 0) || sc.row_begin < prb ||
+        (last - prb) / prs >= h->dd_plan_rows)
+        return fail(SCHW_E_INVALID, "the rows of this call are not covered by the de-duplication plan");
+    if (rgb_pitch == 0) rgb_pitch = 3LL * sc.width;
+    if (cls_pitch == 0) cls_pitch = sc.width;
+    if (rgb_pitch < 3LL * sc.width || cls_pitch < sc.width) return fail(SCHW_E_INVALID, "row pitch smaller than a row");
+    RenderJob job;
+    job.sc = sc; job.tex = d_tex; job.tex_ready = nullptr; job.rgb = d_rgb; job.cls = d_cls;
+    job.rgb_pitch = rgb_pitch; job.cls_pitch = cls_pitch; job.err = &h->ctr->err;
+    job.final_q = x ? x->final_q : nullptr;
+    job.ic = x ? x->ic : nullptr;
+    job.hit = x ? x->hit : nullptr;
+    job.texel = x ? x->texel : nullptr;
+    job.nsteps = x ? x->nsteps : nullptr;
+    job.n = n;
+    job.tile_order = nullptr; job.tiles_per_row = 1; job.qlen = n;
+    CU(cudaMemsetAsync(&h->ctr->pixel_steps, 0, sizeof(unsigned long long), st));
+    dedup_epilogue_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, st>>>(job, (const int *)h->dd_map.p, prb, prs,
+                                                                                  d_fq_all, d_ns_all, h->ctr);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return SCHW_OK;
+}
+
 extern "C" int schw_render_dedup_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex, int row_begin,
                                      int row_end, int row_stride, uint8_t *d_rgb, uint8_t *d_cls,
                                      const schw_ray_outputs *x, void *cuda_stream)
@@ -1501,79 +1753,84 @@ extern "C" int schw_render_dedup_dev(schw_handle *h, const schw_scene *scene, co
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     begin_timed(h, st);
     if (n == 0) { h->last_unique = 0; CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st)); end_timed(h, st); return SCHW_OK; }
-    int *map = nullptr;
     // The geodesics of a frame depend on the camera, the rows and the integrator parameters -- not on the sky patch, the
     // flips or the texture.  A call that differs from the previous one on this handle only in those (an azimuth sweep:
     // SURVEY §8d config 5, "integrate once, 360 lookups") reuses them and runs the per-pixel epilogue alone.
     const double key[16] = {scene->obs[0], scene->obs[1], scene->obs[2], scene->fov, (double)scene->height, (double)scene->width,
                             (double)sc.row_begin, (double)sc.row_stride, (double)sc.nrows, scene->mass, scene->r_max,
                             (double)scene->steps, scene->delta, scene->omega, (double)n, 1.0};
-    const bool reuse = env_switch_on("SCHW_DEDUP_REUSE") && h->dd_valid && memcmp(key, h->dd_key, sizeof(key)) == 0;
+    const bool reuse = env_switch_on("SCHW_DEDUP_REUSE") && h->dd_valid && h->dd_plan_valid && h->dd_world == 1 &&
+                       memcmp(key, h->dd_key, sizeof(key)) == 0;
     if (reuse) {
         CU(cudaStreamWaitEvent(st, h->ev_dd, 0));                       // (the cache may have been filled on another stream)
         CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));          // no step is integrated by this call
-        map = (int *)h->dd_map.p;
     } else {
-    h->dd_valid = false;
-    h->last_unique = 0;
+        h->dd_valid = false;
+        if (!env_switch_on("SCHW_DEDUP_REUSE")) h->dd_plan_valid = false;
+        const bool owns = h->in_pipeline;
+        h->in_pipeline = true;                                          // this entry point owns the timing events
+        rc = dedup_plan(h, scene, row_begin, row_end, row_stride, 1, st);
+        if (!rc) {
+            ENSURE(h->dd_fq, (size_t)h->dd_chunk * 32); ENSURE(h->dd_ns, (size_t)h->dd_chunk * 4);
+            rc = dedup_integrate(h, scene, 0, (double *)h->dd_fq.p, (int32_t *)h->dd_ns.p, st);
+        }
+        h->in_pipeline = owns;
+        if (rc) return rc;
+        CU(cudaEventRecord(h->ev_dd, st));
+        memcpy(h->dd_key, key, sizeof(key));
+        h->dd_valid = true;
+    }
+    rc = dedup_epilogue(h, scene, d_tex, row_begin, row_end, row_stride, d_rgb, 0, d_cls, 0, x, (const double *)h->dd_fq.p,
+                        (const int32_t *)h->dd_ns.p, st);
+    if (rc) return rc;
+    end_timed(h, st);
+    return SCHW_OK;
+}
 
-    // 1. keys -> sort -> run heads -> distinct-ray index of every pixel
-    ENSURE(h->dd_keys, (size_t)n * 8); ENSURE(h->dd_keys2, (size_t)n * 8);
-    ENSURE(h->dd_pix, (size_t)n * 4); ENSURE(h->dd_pix2, (size_t)n * 4);
-    ENSURE(h->dd_head, (size_t)n * 4); ENSURE(h->dd_uid, (size_t)n * 4); ENSURE(h->dd_map, (size_t)n * 4);
-    auto *keys = (unsigned long long *)h->dd_keys.p, *keys2 = (unsigned long long *)h->dd_keys2.p;
-    auto *pix = (unsigned *)h->dd_pix.p, *pix2 = (unsigned *)h->dd_pix2.p;
-    int *head = (int *)h->dd_head.p, *uid1 = (int *)h->dd_uid.p;
-    map = (int *)h->dd_map.p;
-    size_t tmp_sort = 0, tmp_scan = 0;
-    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys2, pix, pix2, (int)n, 0, 64, st));
-    CU(cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, head, uid1, (int)n, st));
-    ENSURE(h->dd_tmp, tmp_sort > tmp_scan ? tmp_sort : tmp_scan);
-    const unsigned blocks = (unsigned)((n + 255) / 256);
-    dedup_key_kernel<<<blocks, 256, 0, st>>>(sc, n, keys, pix);
-    CU(cudaGetLastError());
-    size_t tmp = h->dd_tmp.cap;
-    CU(cub::DeviceRadixSort::SortPairs(h->dd_tmp.p, tmp, keys, keys2, pix, pix2, (int)n, 0, 64, st));
-    dedup_heads_kernel<<<blocks, 256, 0, st>>>(keys2, n, head);
-    CU(cudaGetLastError());
-    tmp = h->dd_tmp.cap;
-    CU(cub::DeviceScan::InclusiveSum(h->dd_tmp.p, tmp, head, uid1, (int)n, st));
-    int n_unique = 0;
-    CU(cudaMemcpyAsync(&n_unique, uid1 + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (n_unique <= 0 || n_unique > n) return fail(SCHW_E_CUDA, "de-duplication produced an impossible ray count");
-    h->last_unique = n_unique;
-
-    // 2. the distinct rays, integrated once each
-    ENSURE(h->dd_q0, (size_t)n_unique * 32); ENSURE(h->dd_p0, (size_t)n_unique * 32);
-    ENSURE(h->dd_fq, (size_t)n_unique * 32); ENSURE(h->dd_ns, (size_t)n_unique * 4);
-    dedup_scatter_kernel<<<blocks, 256, 0, st>>>(sc, n, pix2, head, uid1, map, (double *)h->dd_q0.p, (double *)h->dd_p0.p);
-    CU(cudaGetLastError());
-    h->launches += 5;                                   // key, sort, heads, scan, scatter
+// The three stages for the ranks of a multi-GPU job (schw_b200/multigpu.py): every rank plans the WHOLE frame (identical
+// on all ranks: the kernels and cub's radix sort are deterministic), integrates its share of the distinct rays into its
+// slots of the (world*chunk, 4) / (world*chunk) arrays, the caller all-gathers those, and every rank runs the epilogue
+// of its own rows.
+extern "C" int schw_dedup_plan_dev(schw_handle *h, const schw_scene *scene, int world, uint64_t *n_unique, uint64_t *chunk,
+                                   void *cuda_stream)
+{
+    if (!h || !scene) return fail(SCHW_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    begin_timed(h, st);
     h->in_pipeline = true;
-    rc = integrate_batch_impl(h, (const double *)h->dd_q0.p, (const double *)h->dd_p0.p, n_unique, scene->steps, scene->delta,
-                              2.0 * scene->mass, scene->r_max, scene->omega, (double *)h->dd_fq.p, (int32_t *)h->dd_ns.p, st);
+    int rc = dedup_plan(h, scene, 0, scene->height, 1, world, st);
     h->in_pipeline = false;
     if (rc) return rc;
-    CU(cudaEventRecord(h->ev_dd, st));
-    memcpy(h->dd_key, key, sizeof(key));
-    h->dd_valid = true;
-    }
+    end_timed(h, st);
+    if (n_unique) *n_unique = (uint64_t)h->last_unique;
+    if (chunk) *chunk = (uint64_t)h->dd_chunk;
+    return SCHW_OK;
+}
 
-    // 3. per-pixel epilogue
-    RenderJob job;
-    job.sc = sc; job.tex = d_tex; job.tex_ready = nullptr; job.rgb = d_rgb; job.cls = d_cls;
-    job.final_q = x ? x->final_q : nullptr;
-    job.ic = x ? x->ic : nullptr;
-    job.hit = x ? x->hit : nullptr;
-    job.texel = x ? x->texel : nullptr;
-    job.nsteps = x ? x->nsteps : nullptr;
-    job.n = n;
-    job.tile_order = nullptr; job.tiles_per_row = 1; job.qlen = n;
-    dedup_epilogue_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, st>>>(job, map, (const double *)h->dd_fq.p,
-                                                                                  (const int32_t *)h->dd_ns.p, h->ctr);
-    h->launches += 1;
-    CU(cudaGetLastError());
+extern "C" int schw_dedup_integrate_dev(schw_handle *h, const schw_scene *scene, int rank, double *d_fq_all,
+                                        int32_t *d_ns_all, void *cuda_stream)
+{
+    if (!h || !scene) return fail(SCHW_E_INVALID, "null argument");
+    if (!d_fq_all || !d_ns_all) return fail(SCHW_E_INVALID, "null array");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    return dedup_integrate(h, scene, rank, d_fq_all, d_ns_all, st);
+}
+
+extern "C" int schw_dedup_epilogue_dev(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex, int row_begin,
+                                       int row_end, int row_stride, uint8_t *d_rgb, int64_t rgb_row_pitch, uint8_t *d_cls,
+                                       int64_t cls_row_pitch, const schw_ray_outputs *x, const double *d_fq_all,
+                                       const int32_t *d_ns_all, void *cuda_stream)
+{
+    if (!h || !scene) return fail(SCHW_E_INVALID, "null argument");
+    if (!d_fq_all || !d_ns_all) return fail(SCHW_E_INVALID, "null array");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    begin_timed(h, st);
+    int rc = dedup_epilogue(h, scene, d_tex, row_begin, row_end, row_stride, d_rgb, rgb_row_pitch, d_cls, cls_row_pitch, x,
+                            d_fq_all, d_ns_all, st);
+    if (rc) return rc;
     end_timed(h, st);
     return SCHW_OK;
 }
@@ -1589,6 +1846,7 @@ extern "C" int schw_render_dedup(schw_handle *h, const schw_scene *scene, const 
     CU(cudaSetDevice(h->device));
     const int nrows = row_end > row_begin ? (row_end - row_begin + row_stride - 1) / row_stride : 0;
     const size_t n = (size_t)nrows * scene->width;
+    if (n > 0x7fffffffULL) return fail(SCHW_E_INVALID, "more than 2^31-1 rays in one call (the kernel indexes rays with 32-bit integers)");
     if (n > 0 && (!rgb || !cls)) return fail(SCHW_E_INVALID, "null output");
     cudaStream_t st = h->stream;
     const size_t tb = (size_t)scene->height * scene->width * 3;
@@ -1614,8 +1872,7 @@ extern "C" int schw_render_dedup(schw_handle *h, const schw_scene *scene, const 
         if (d.texel) CU(cudaMemcpyAsync(x->texel, d.texel, n * 8, cudaMemcpyDeviceToHost, st));
         if (d.nsteps) CU(cudaMemcpyAsync(x->nsteps, d.nsteps, n * 4, cudaMemcpyDeviceToHost, st));
     }
-    CU(cudaStreamSynchronize(st));
-    return SCHW_OK;
+    return sync_and_check(h, st);
 }
 
 // Distinct rays integrated by the last schw_render_dedup* call, and the steps summed over its pixels (what one ray
@@ -1647,6 +1904,70 @@ static double pymod_host(double a, double b)
     return m;
 }
 
+// sphere + patch + texture part of FlatParams (background.py:60-66 / cuda_geodesic.py:65-78)
+static void flat_patch_params(FlatParams &fp, const double obs[3], double boundary_radius, double pct, double pcp, double pst,
+                              double psp, int flip_theta, int flip_phi, int tex_h, int tex_w)
+{
+    for (int a = 0; a < 3; ++a) fp.obs[a] = obs[a];
+    fp.r2 = boundary_radius * boundary_radius;
+    fp.obs_dot_obs = obs[0] * obs[0] + obs[1] * obs[1] + obs[2] * obs[2];
+    fp.theta0 = pct - pst / 2;
+    fp.theta1 = pct + pst / 2;
+    fp.phi0 = pcp - psp / 2;
+    fp.phi1 = pcp + psp / 2;
+    const double two_pi = 2 * M_PI;
+    fp.phi_span = pymod_host(fp.phi1 - fp.phi0, two_pi);
+    if (fp.phi_span == 0) fp.phi_span = two_pi;
+    fp.phi0m = pymod_host(fp.phi0, two_pi);
+    fp.phi1m = pymod_host(fp.phi1, two_pi);
+    fp.height = tex_h; fp.width = tex_w; fp.flip_theta = flip_theta; fp.flip_phi = flip_phi;
+}
+
+extern "C" int schw_flat_raytrace(schw_handle *h, const double *obs, const double *ray_dirs, int64_t n, double boundary_radius,
+                                  double patch_center_theta, double patch_center_phi, double patch_size_theta,
+                                  double patch_size_phi, int flip_theta, int flip_phi, const uint8_t *bg, int tex_h, int tex_w,
+                                  uint8_t *out_rgb, const int32_t *sampled_indices, int64_t n_sampled, int64_t n_points,
+                                  double *out_trajs)
+{
+    if (!h || !obs || !bg) return fail(SCHW_E_INVALID, "null argument");
+    if (n < 0 || n > 0x7fffffffLL || n_sampled < 0 || n_points < 0 || n_sampled * n_points > 0x7fffffffLL)
+        return fail(SCHW_E_INVALID, "bad size");
+    if (tex_h <= 0 || tex_w <= 0) return fail(SCHW_E_INVALID, "texture size must be positive");
+    if (n > 0 && (!ray_dirs || !out_rgb)) return fail(SCHW_E_INVALID, "null array");
+    if (n_sampled > 0 && n_points > 0 && (!sampled_indices || !out_trajs)) return fail(SCHW_E_INVALID, "null trajectory array");
+    CU(cudaSetDevice(h->device));
+    FlatParams fp;
+    memset(&fp, 0, sizeof(fp));
+    flat_patch_params(fp, obs, boundary_radius, patch_center_theta, patch_center_phi, patch_size_theta, patch_size_phi,
+                      flip_theta, flip_phi, tex_h, tex_w);
+    if (n == 0) return SCHW_OK;
+    cudaStream_t st = h->stream;
+    const size_t tb = (size_t)tex_h * tex_w * 3, nt = (size_t)n_sampled * n_points;
+    ENSURE(h->tex, tb); ENSURE(h->rgb, (size_t)n * 3 + 1); ENSURE(h->in_a, (size_t)n * 24);
+    CU(cudaMemcpyAsync(h->tex.p, bg, tb, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->in_a.p, ray_dirs, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    begin_timed(h, st);
+    flat_dirs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fp, (const double *)h->in_a.p, (long long)n,
+                                                                   (const uint8_t *)h->tex.p, (uint8_t *)h->rgb.p);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    if (nt > 0) {
+        ENSURE(h->in_c, (size_t)n_sampled * sizeof(int32_t)); ENSURE(h->traj, nt * 24);
+        CU(cudaMemcpyAsync(h->in_c.p, sampled_indices, (size_t)n_sampled * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(h->traj.p, 0, nt * 24, st));
+        flat_traj_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(fp, (const double *)h->in_a.p, (long long)n,
+                                                                        (const int32_t *)h->in_c.p, (int)n_sampled, (int)n_points,
+                                                                        (double *)h->traj.p);
+        h->launches += 1;
+        CU(cudaGetLastError());
+    }
+    end_timed(h, st);
+    CU(cudaMemcpyAsync(out_rgb, h->rgb.p, (size_t)n * 3, cudaMemcpyDeviceToHost, st));
+    if (nt > 0) CU(cudaMemcpyAsync(out_trajs, h->traj.p, nt * 24, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SCHW_OK;
+}
+
 extern "C" int schw_flat_render(schw_handle *h, const schw_scene *s, const uint8_t *tex, uint8_t *rgb)
 {
     if (!h || !s || !tex || !rgb) return fail(SCHW_E_INVALID, "null argument");
@@ -1668,21 +1989,11 @@ extern "C" int schw_flat_render(schw_handle *h, const schw_scene *s, const uint8
     double un = sqrt(up[0] * up[0] + up[1] * up[1] + up[2] * up[2]);
     for (int a = 0; a < 3; ++a) up[a] /= un;
     const double plane_dist = 0.2 * nrm;
-    for (int a = 0; a < 3; ++a) { fp.obs[a] = s->obs[a]; fp.pc[a] = s->obs[a] + axis[a] * plane_dist; fp.right[a] = right[a]; fp.up[a] = up[a]; }
+    for (int a = 0; a < 3; ++a) { fp.pc[a] = s->obs[a] + axis[a] * plane_dist; fp.right[a] = right[a]; fp.up[a] = up[a]; }
     fp.plane_width = 2 * plane_dist * tan(s->fov / 2);
     fp.plane_height = fp.plane_width * ((double)s->height / (double)s->width);
-    fp.r2 = s->r_max * s->r_max;
-    fp.obs_dot_obs = s->obs[0] * s->obs[0] + s->obs[1] * s->obs[1] + s->obs[2] * s->obs[2];
-    fp.theta0 = s->patch_center_theta - s->patch_size_theta / 2;
-    fp.theta1 = s->patch_center_theta + s->patch_size_theta / 2;
-    fp.phi0 = s->patch_center_phi - s->patch_size_phi / 2;
-    fp.phi1 = s->patch_center_phi + s->patch_size_phi / 2;
-    const double two_pi = 2 * M_PI;
-    fp.phi_span = pymod_host(fp.phi1 - fp.phi0, two_pi);
-    if (fp.phi_span == 0) fp.phi_span = two_pi;
-    fp.phi0m = pymod_host(fp.phi0, two_pi);
-    fp.phi1m = pymod_host(fp.phi1, two_pi);
-    fp.height = s->height; fp.width = s->width; fp.flip_theta = s->flip_theta; fp.flip_phi = s->flip_phi;
+    flat_patch_params(fp, s->obs, s->r_max, s->patch_center_theta, s->patch_center_phi, s->patch_size_theta, s->patch_size_phi,
+                      s->flip_theta, s->flip_phi, s->height, s->width);
     const size_t n = (size_t)s->height * s->width;
     cudaStream_t st = h->stream;
     ENSURE(h->tex, n * 3); ENSURE(h->rgb, n * 3 + 1);

@@ -26,6 +26,8 @@ EXPORTS = (
     "schw_flat_render", "schw_fp64_peak_probe", "schw_math_probe", "schw_last_counters",
     "schw_host_alloc", "schw_host_free", "schw_set_tex_ready_flag", "schw_debug_step_params",
     "schw_render_dedup", "schw_render_dedup_dev", "schw_last_dedup_stats",
+    "schw_render_dev_pitched", "schw_last_status", "schw_flat_raytrace",
+    "schw_dedup_plan_dev", "schw_dedup_integrate_dev", "schw_dedup_epilogue_dev", "schw_observer_q0",
 )
 
 
@@ -94,6 +96,13 @@ def load():
     L.schw_classify.argtypes = [vp, scp, dp, dp, dp, i64, vp, vp, vp, dp, vp]
     L.schw_render.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop]
     L.schw_render_dev.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop, vp]
+    L.schw_render_dev_pitched.argtypes = [vp, scp, vp, i32, i32, i32, vp, i64, vp, i64, xop, vp]
+    L.schw_last_status.argtypes = [vp]
+    L.schw_flat_raytrace.argtypes = [vp, dp, dp, i64, dbl, dbl, dbl, dbl, dbl, i32, i32, vp, i32, i32, vp, vp, i64, i64, dp]
+    L.schw_observer_q0.argtypes = [scp, dp]
+    L.schw_dedup_plan_dev.argtypes = [vp, scp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp]
+    L.schw_dedup_integrate_dev.argtypes = [vp, scp, i32, vp, vp, vp]
+    L.schw_dedup_epilogue_dev.argtypes = [vp, scp, vp, i32, i32, i32, vp, i64, vp, i64, xop, vp, vp, vp]
     L.schw_render_dedup.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop]
     L.schw_render_dedup_dev.argtypes = [vp, scp, vp, i32, i32, i32, vp, vp, xop, vp]
     L.schw_last_dedup_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -192,6 +201,13 @@ def make_scene(obs=(30.0, 0.0, 0.0), fov=np.radians(80.0), height=400, width=400
     s.patch_size_theta = float(patch_size_theta); s.patch_size_phi = float(patch_size_phi)
     s.flip_theta = int(bool(flip_theta)); s.flip_phi = int(bool(flip_phi)); s.has_texture = int(bool(has_texture))
     return s
+
+
+def observer_q0(scene):
+    """q0 = (0, r_obs, theta_obs, phi_obs) of the scene's camera rays (host arithmetic, no device)."""
+    q0 = np.zeros(4)
+    _check(load().schw_observer_q0(C.byref(scene), _p(q0)))
+    return q0
 
 
 class Handle:
@@ -356,6 +372,21 @@ class Handle:
                                        row_stride, C.c_void_p(d_rgb), C.c_void_p(d_cls), C.byref(x),
                                        C.c_void_p(stream or None)))
 
+    def render_dev_pitched(self, scene, d_tex, row_begin, row_end, row_stride, d_rgb, rgb_pitch, d_cls, cls_pitch, stream=0,
+                           d_final_q=0, d_ic=0, d_hit=0, d_texel=0, d_nsteps=0, d_tex_ready=0):
+        """render_dev with explicit output row pitches in bytes (0 = packed), e.g. rgb and class side by side in the
+        (rows, 4w) block of the multi-GPU gather."""
+        if d_tex_ready:
+            _check(self._L.schw_set_tex_ready_flag(self._h, C.c_void_p(d_tex_ready)))
+        x = SchwRayOutputs(d_final_q or None, d_ic or None, d_hit or None, d_texel or None, d_nsteps or None)
+        _check(self._L.schw_render_dev_pitched(self._h, C.byref(scene), C.c_void_p(d_tex or None), row_begin, row_end,
+                                               row_stride, C.c_void_p(d_rgb), int(rgb_pitch), C.c_void_p(d_cls),
+                                               int(cls_pitch), C.byref(x), C.c_void_p(stream or None)))
+
+    def last_status(self):
+        """Waits for the last enqueue-only call and raises what its device code flagged (see schw_last_status)."""
+        _check(self._L.schw_last_status(self._h))
+
     def render_dedup_dev(self, scene, d_tex, row_begin, row_end, row_stride, d_rgb, d_cls, stream=0,
                          d_final_q=0, d_ic=0, d_hit=0, d_texel=0, d_nsteps=0):
         """Device-pointer de-duplicated render (opt-in).  Synchronises the stream once unless the
@@ -365,11 +396,53 @@ class Handle:
                                              row_stride, C.c_void_p(d_rgb), C.c_void_p(d_cls), C.byref(x),
                                              C.c_void_p(stream or None)))
 
+    # -- de-duplicated render, stage by stage (the ranks of a multi-GPU job share the integration) ----------
+    def dedup_plan_dev(self, scene, world, stream=0):
+        """Distinct camera rays of the WHOLE frame; returns (n_unique, chunk).  Synchronises the stream once."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(self._L.schw_dedup_plan_dev(self._h, C.byref(scene), int(world), C.byref(a), C.byref(b),
+                                           C.c_void_p(stream or None)))
+        return int(a.value), int(b.value)
+
+    def dedup_integrate_dev(self, scene, rank, d_fq_all, d_ns_all, stream=0):
+        _check(self._L.schw_dedup_integrate_dev(self._h, C.byref(scene), int(rank), C.c_void_p(d_fq_all),
+                                                C.c_void_p(d_ns_all), C.c_void_p(stream or None)))
+
+    def dedup_epilogue_dev(self, scene, d_tex, row_begin, row_end, row_stride, d_rgb, rgb_pitch, d_cls, cls_pitch,
+                           d_fq_all, d_ns_all, stream=0, d_final_q=0, d_ic=0, d_hit=0, d_texel=0, d_nsteps=0):
+        x = SchwRayOutputs(d_final_q or None, d_ic or None, d_hit or None, d_texel or None, d_nsteps or None)
+        _check(self._L.schw_dedup_epilogue_dev(self._h, C.byref(scene), C.c_void_p(d_tex or None), row_begin, row_end,
+                                               row_stride, C.c_void_p(d_rgb), int(rgb_pitch), C.c_void_p(d_cls),
+                                               int(cls_pitch), C.byref(x), C.c_void_p(d_fq_all), C.c_void_p(d_ns_all),
+                                               C.c_void_p(stream or None)))
+
     def flat_render(self, scene, tex):
         tex = np.ascontiguousarray(tex, np.uint8)
         rgb = np.zeros((scene.height, scene.width, 3), np.uint8)
         _check(self._L.schw_flat_render(self._h, C.byref(scene), _p(tex), _p(rgb)))
         return rgb
+
+
+    def flat_raytrace(self, obs_pos, ray_dirs, boundary_radius, patch_center_theta, patch_center_phi, patch_size_theta,
+                      patch_size_phi, flip_theta, flip_phi, bg_array, sampled_indices=None, n_points=100):
+        """cuda_flat_raytrace[_with_trajectories] (simulation/cuda_geodesic.py:214-292) on caller-supplied directions."""
+        obs = np.ascontiguousarray(obs_pos, np.float64); dirs = np.ascontiguousarray(ray_dirs, np.float64).reshape(-1, 3)
+        bg = np.ascontiguousarray(bg_array, np.uint8)
+        n = dirs.shape[0]
+        out = np.zeros((n, 3), np.uint8)
+        if sampled_indices is None:
+            _check(self._L.schw_flat_raytrace(self._h, _p(obs), _p(dirs), n, float(boundary_radius), float(patch_center_theta),
+                                              float(patch_center_phi), float(patch_size_theta), float(patch_size_phi),
+                                              int(bool(flip_theta)), int(bool(flip_phi)), _p(bg), bg.shape[0], bg.shape[1],
+                                              _p(out), None, 0, 0, None))
+            return out
+        idx = np.ascontiguousarray(sampled_indices, np.int32)
+        trajs = np.zeros((idx.size, int(n_points), 3), np.float64)
+        _check(self._L.schw_flat_raytrace(self._h, _p(obs), _p(dirs), n, float(boundary_radius), float(patch_center_theta),
+                                          float(patch_center_phi), float(patch_size_theta), float(patch_size_phi),
+                                          int(bool(flip_theta)), int(bool(flip_phi)), _p(bg), bg.shape[0], bg.shape[1],
+                                          _p(out), _p(idx), idx.size, int(n_points), _p(trajs)))
+        return out, trajs
 
 
 _default = {}

@@ -32,8 +32,25 @@ class CUDASchwarzschildIntegrator:
                                                                  self.r_max, self.omega)
 
 
-def _flat_scene(obs_pos, h, w, fov, boundary_radius, pct, pcp, pst, psp, flip_theta, flip_phi):
-    from schw_b200 import make_scene
-    return make_scene(obs=obs_pos, fov=fov, height=h, width=w, r_max=boundary_radius, patch_center_theta=pct,
-                      patch_center_phi=pcp, patch_size_theta=pst, patch_size_phi=psp, flip_theta=flip_theta,
-                      flip_phi=flip_phi)
+def cuda_flat_raytrace(obs_pos, ray_dirs, boundary_radius,
+                       patch_center_theta, patch_center_phi,
+                       patch_size_theta, patch_size_phi,
+                       flip_theta, flip_phi,
+                       bg_array):
+    """Flat-space ray tracing of caller-supplied unit directions; returns the flattened (N,3) uint8 RGB array
+    (cuda_geodesic.py:214-250, as imported by simulation/background.py:95)."""
+    return default_handle().flat_raytrace(obs_pos, ray_dirs, boundary_radius, patch_center_theta, patch_center_phi,
+                                          patch_size_theta, patch_size_phi, flip_theta, flip_phi, bg_array)
+
+
+def cuda_flat_raytrace_with_trajectories(obs_pos, ray_dirs, boundary_radius,
+                                         patch_center_theta, patch_center_phi,
+                                         patch_size_theta, patch_size_phi,
+                                         flip_theta, flip_phi,
+                                         bg_array,
+                                         sampled_indices, n_points=100):
+    """Same, plus `n_points` samples along each ray listed in `sampled_indices` (flat indices): returns
+    (image (N,3) uint8, trajectories (len(sampled_indices), n_points, 3) float64)  (cuda_geodesic.py:252-292)."""
+    return default_handle().flat_raytrace(obs_pos, ray_dirs, boundary_radius, patch_center_theta, patch_center_phi,
+                                          patch_size_theta, patch_size_phi, flip_theta, flip_phi, bg_array,
+                                          sampled_indices=list(sampled_indices), n_points=n_points)

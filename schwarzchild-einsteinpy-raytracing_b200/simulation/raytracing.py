@@ -67,10 +67,11 @@ def run_manual_simulation(
     """
     logging.info("Starting manual ray tracing simulation...")
     h, w = observer.image_size
-    if not use_cuda:
-        # reference: the CPU branch is `pass` and crashes with NameError at raytracing.py:131
-        raise RuntimeError("run_manual_simulation: only the CUDA path exists (use_cuda=True); there is no CPU fallback")
-    if boundary_radius is None:
+    if not use_cuda and n_samples > 0:
+        # reference: without use_cuda nothing is integrated (the CPU branch is `pass`, raytracing.py:301-302) and the
+        # sampled-trajectory block dies on the undefined q0s (raytracing.py:131).  There is no CPU fallback here either.
+        raise NameError("name 'q0s' is not defined (run_manual_simulation: only the CUDA path exists, pass use_cuda=True)")
+    if use_cuda and boundary_radius is None:
         raise TypeError("boundary_radius must be given (the reference passes it to the integrator as r_max)")
     bg_array = _load_texture(background_path, h, w)
     img = np.zeros((h, w, 3), dtype=np.uint8)
@@ -84,7 +85,8 @@ def run_manual_simulation(
         if dist_info()[1] > 1:                            # every rank must agree on the sampled pixels
             sampled_indices = set(broadcast_object(sorted(sampled_indices)))
     if not (n_samples > 0 and sampled_indices):
-        # reference quirk (App. D-3): the whole image-building block is nested under this test
+        # reference quirk (App. D-3): the whole image-building block is nested under this test, so with n_samples == 0
+        # -- with or without use_cuda -- the frame stays black (raytracing.py:129,304-314)
         print("Summary counts not available (CPU fallback mode).")
         return img
 
@@ -92,7 +94,11 @@ def run_manual_simulation(
                             patch_size_theta, patch_size_phi, flip_theta, flip_phi, bg_array is not None)
     logging.info("Using CUDA Schwarzschild integrator for curved rays ...")
     from schw_b200.multigpu import render_frame
-    out = render_frame(scene, bg_array, extras=True, dedup=dedup)
+    # under torchrun the frame and its per-ray diagnostics are gathered to rank 0 only (root=0): it alone writes the
+    # files and returns the image; the other ranks return (None, [])
+    out = render_frame(scene, bg_array, extras=True, dedup=dedup, root=0)
+    if out["rgb"] is None:
+        return None, []
     img = out["rgb"]
     cls = out["cls"].reshape(-1)
     ic = out["ic"]
@@ -117,8 +123,7 @@ def run_manual_simulation(
         c, sn = np.cos(betas[flat]), np.sin(betas[flat])
         sampled_traj_data.append(np.stack([x, c * y - sn * z, sn * y + c * z], axis=1).astype(np.float64))
 
-    from schw_b200.multigpu import dist_info
-    if write_outputs and dist_info()[0] == 0:           # under torchrun only rank 0 writes the files
+    if write_outputs:                                   # (under torchrun only rank 0 gets here)
         import pandas as pd
         _save_png('images/manual_output.png', img)
         logging.info("Saved manual_output.png")

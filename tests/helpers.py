@@ -99,3 +99,52 @@ def flat_scene_kwargs(cfg):
                 r_max=float(c["r_max"]), patch_center_theta=float(pct), patch_center_phi=float(pcp),
                 patch_size_theta=np.deg2rad(c["pst"]), patch_size_phi=np.deg2rad(c["psp"]),
                 flip_theta=c["flt"], flip_phi=c["flp"])
+
+
+def flat_texel_coords(k):
+    """Per pixel of the flat render (background.py:99-132, NumPy FP64): continuous texel coordinates before the truncating
+    int(), the hit angles and the patch bounds -- to decide whether a pixel that differs between two implementations
+    sits on a truncation / patch boundary (where a last-bit difference of acos/atan2 legitimately flips it)."""
+    h, w = k["height"], k["width"]
+    obs = np.array(k["obs"], np.float64)
+    axis = -obs / np.linalg.norm(obs)
+    up_guess = np.array([0.0, 0.0, 1.0])
+    if np.allclose(np.cross(axis, up_guess), 0):
+        up_guess = np.array([0.0, 1.0, 0.0])
+    right = np.cross(up_guess, axis); right /= np.linalg.norm(right)
+    up = np.cross(axis, right); up /= np.linalg.norm(up)
+    pd_ = 0.2 * np.linalg.norm(obs)
+    pw = 2 * pd_ * np.tan(k["fov"] / 2); ph = pw * (h / w)
+    jj, ii = np.meshgrid(np.arange(w), np.arange(h))
+    u = (jj + 0.5) / w - 0.5; v = (ii + 0.5) / h - 0.5
+    px = (obs + axis * pd_)[None, None, :] + (u * pw)[..., None] * right + (v * ph)[..., None] * up
+    d = px - obs; d /= np.linalg.norm(d, axis=2, keepdims=True)
+    b = 2 * (d @ obs); c = obs @ obs - k["r_max"] ** 2
+    disc = b * b - 4 * c
+    t = (-b + np.sqrt(np.maximum(disc, 0))) / 2
+    hit = obs + t[..., None] * d
+    r = np.linalg.norm(hit, axis=2)
+    theta = np.arccos(np.clip(hit[..., 2] / r, -1, 1)); phi = np.arctan2(hit[..., 1], hit[..., 0])
+    th0 = k["patch_center_theta"] - k["patch_size_theta"] / 2; th1 = k["patch_center_theta"] + k["patch_size_theta"] / 2
+    ph0 = k["patch_center_phi"] - k["patch_size_phi"] / 2; ph1 = k["patch_center_phi"] + k["patch_size_phi"] / 2
+    span = (ph1 - ph0) % (2 * np.pi) or 2 * np.pi
+    tmap = (np.pi - theta) if k.get("flip_theta") else theta
+    pmap = -phi if k.get("flip_phi") else phi
+    fu = (tmap - th0) / (th1 - th0) * (h - 1)
+    fv = ((pmap - ph0) % (2 * np.pi)) / span * (w - 1)
+    return dict(fu=fu, fv=fv, theta=theta, phi=phi % (2 * np.pi), th0=th0, th1=th1, ph0=ph0 % (2 * np.pi), ph1=ph1 % (2 * np.pi),
+                disc=disc)
+
+
+def flat_mismatch_explained(k, a, b, eps=1e-7):
+    """Every pixel where the flat renders a and b differ lies within eps of a truncation boundary of the texel map, of a
+    patch edge, or of the tangent rays of the boundary sphere.  Returns (n_differing, n_unexplained)."""
+    diff = np.any(a != b, axis=2)
+    if not diff.any():
+        return 0, 0
+    c = flat_texel_coords(k)
+    near_int = lambda x: np.abs(x - np.round(x)) < eps * max(1.0, float(np.max(np.abs(x))))
+    ang = lambda x, y: np.abs((x - y + np.pi) % (2 * np.pi) - np.pi) < eps
+    ok = (near_int(c["fu"]) | near_int(c["fv"]) | (np.abs(c["theta"] - c["th0"]) < eps) | (np.abs(c["theta"] - c["th1"]) < eps)
+          | ang(c["phi"], c["ph0"]) | ang(c["phi"], c["ph1"]) | (np.abs(c["disc"]) < eps))
+    return int(diff.sum()), int((diff & ~ok).sum())

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     nm = subprocess.check_output(["nm", "-D", "--defined-only", schw_b200.native.LIB_PATH], text=True)
     exported = set(re.findall(r" T (schw_\w+)", nm))
     assert exported == set(names), exported ^ set(names)
-    assert lib.schw_abi_version() == 1
+    assert lib.schw_abi_version() == 2
 
 
 def test_scene_struct_layout_matches_header():

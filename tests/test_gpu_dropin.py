@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, relerr
-from helpers import flat_scene_kwargs, in_band_g, near_rounding_boundary, scene_kwargs_from_cfg, state_close, texel_coords
+from helpers import flat_mismatch_explained, flat_scene_kwargs, in_band_g, near_rounding_boundary, scene_kwargs_from_cfg, state_close, texel_coords
 
 pytestmark = pytest.mark.gpu
 
@@ -103,15 +103,19 @@ def test_flat_render_vs_reference_and_oracle(handle, orc, golden, tmp_path):
         g = golden(f"flat_{name}.npz")
         kw = flat_scene_kwargs(g["cfg"])
         img = handle.flat_render(schw_b200.make_scene(**kw), g["bg_array"])
-        assert np.any(img != g["img"], axis=2).mean() <= 2e-3, name
-        assert np.any(img != orc.flat_render(orc.make_scene(**kw), g["bg_array"]), axis=2).mean() <= 2e-3
+        # pixels may differ from the reference's image only ON a truncation boundary of its int() texel map (or a patch
+        # edge), where the last bit of acos/atan2 decides -- checked per pixel, not assumed
+        for other in (g["img"], orc.flat_render(orc.make_scene(**kw), g["bg_array"])):
+            ndiff, unexplained = flat_mismatch_explained(kw, img, other)
+            assert unexplained == 0 and ndiff <= 2e-3 * img.shape[0] * img.shape[1], (name, ndiff, unexplained)
     # bigger frame vs the oracle
     from helpers import synthetic_sky
     tex = synthetic_sky(270, 480, 3)
     kw = dict(obs=(20.0, 0, 0), fov=np.radians(90), height=270, width=480, r_max=21.0, patch_center_theta=np.deg2rad(100),
               patch_center_phi=np.deg2rad(205), patch_size_theta=np.deg2rad(126), patch_size_phi=np.deg2rad(224), flip_phi=True)
     a = handle.flat_render(schw_b200.make_scene(**kw), tex); b = orc.flat_render(orc.make_scene(**kw), tex)
-    assert np.any(a != b, axis=2).mean() < 1e-3 and a.any()
+    ndiff, unexplained = flat_mismatch_explained(kw, a, b)
+    assert unexplained == 0 and ndiff < 1e-3 * a.shape[0] * a.shape[1] and a.any(), (ndiff, unexplained)
     # the entry point with the reference's signature and files
     c = json.loads(str(golden("flat_F2.npz")["cfg"]))
     obs = Observer(position=np.array([c["obs_x"], 0, 0]), fov=np.radians(c["fov"]), image_size=(c["h"], c["w"]))
@@ -125,6 +129,46 @@ def test_flat_render_vs_reference_and_oracle(handle, orc, golden, tmp_path):
     assert np.any(np.array(Image.open(out).convert("RGB")) != golden("flat_F2.npz")["img"], axis=2).mean() <= 2e-3
     assert len(trajs) == 4 and all(t.shape == (100, 3) for t in trajs)
     assert all(abs(np.linalg.norm(t[-1]) - c["r_max"]) < 1e-9 for t in trajs)
+
+
+def test_cuda_flat_raytrace_wrappers(handle, orc):
+    """`from simulation.cuda_geodesic import cuda_flat_raytrace[_with_trajectories]` as background.py:77,95 uses them:
+    caller-supplied unit directions, flattened (N,3) image, (S,n_points,3) straight-line samples."""
+    import schw_b200
+    from simulation.cuda_geodesic import cuda_flat_raytrace, cuda_flat_raytrace_with_trajectories
+    from helpers import synthetic_sky
+    h, w = 120, 200
+    tex = synthetic_sky(h, w, 7)
+    kw = dict(obs=(25.0, 0, 0), fov=np.radians(75), height=h, width=w, r_max=40.0, patch_center_theta=np.deg2rad(95),
+              patch_center_phi=np.deg2rad(170), patch_size_theta=np.deg2rad(150), patch_size_phi=np.deg2rad(300), flip_theta=True)
+    # ray directions exactly as background.py:80-91 builds them
+    obs = np.array(kw["obs"]); axis = -obs / np.linalg.norm(obs)
+    right = np.cross([0.0, 0.0, 1.0], axis); right /= np.linalg.norm(right)
+    up = np.cross(axis, right); up /= np.linalg.norm(up)
+    pc = obs + axis * 0.2 * np.linalg.norm(obs)
+    pw = 2 * 0.2 * np.linalg.norm(obs) * np.tan(kw["fov"] / 2); ph = pw * (h / w)
+    jj, ii = np.meshgrid(np.arange(w), np.arange(h))
+    px = pc[None, None, :] + (((jj + 0.5) / w - 0.5) * pw)[..., None] * right + (((ii + 0.5) / h - 0.5) * ph)[..., None] * up
+    dirs = px - obs[None, None, :]
+    dirs = (dirs / np.linalg.norm(dirs, axis=2, keepdims=True)).reshape(-1, 3)
+    patch = (kw["patch_center_theta"], kw["patch_center_phi"], kw["patch_size_theta"], kw["patch_size_phi"], True, False)
+    flat = cuda_flat_raytrace(obs, dirs, kw["r_max"], *patch, tex)
+    assert flat.shape == (h * w, 3) and flat.dtype == np.uint8 and flat.any()
+    img = flat.reshape(h, w, 3)
+    for other in (handle.flat_render(schw_b200.make_scene(**kw), tex), orc.flat_render(orc.make_scene(**kw), tex)):
+        ndiff, unexplained = flat_mismatch_explained(kw, img, other)
+        assert unexplained == 0 and ndiff <= 2e-3 * h * w, (ndiff, unexplained)
+    picks = [0, 5 * w + 17, h * w - 1, 5 * w + 17]                      # a duplicate index fills both of its rows
+    flat2, trajs = cuda_flat_raytrace_with_trajectories(obs, dirs, kw["r_max"], *patch, tex, picks, n_points=100)
+    assert np.array_equal(flat2, flat) and trajs.shape == (4, 100, 3)
+    for s, k in enumerate(picks):
+        d = dirs[k]; b = 2 * obs @ d; c = obs @ obs - kw["r_max"] ** 2
+        hit = obs + (-b + np.sqrt(b * b - 4 * (d @ d) * c)) / (2 * (d @ d)) * d
+        want = obs[None, :] + (np.arange(100) / 99.0)[:, None] * (hit - obs)[None, :]
+        assert np.allclose(trajs[s], want, rtol=0, atol=1e-12)
+    # a ray that misses the sphere (observer outside it, pointing away): black pixel, zero trajectory rows
+    miss, tr = cuda_flat_raytrace_with_trajectories(np.array([50.0, 0, 0]), np.array([[1.0, 0, 0]]), 10.0, *patch, tex, [0], n_points=5)
+    assert not miss.any() and not tr.any()
 
 
 def test_main_entry_point_end_to_end(tmp_path, monkeypatch, capsys):

@@ -1,5 +1,6 @@
 """Two real ranks (one process per GPU, NCCL): `render_frame` — row-cyclic shards, one device-side
-all_gather, un-permutation — must reproduce the single-GPU frame bit for bit, diagnostics included.
+all_gather, un-permutation — must reproduce the single-GPU frame bit for bit, diagnostics included; so must the
+opt-in de-duplicated render, in which the ranks share the integration of the distinct camera rays.
 Skipped on a one-GPU box (NCCL cannot put two ranks on one device); CPU coverage of the same host
 logic is tests/test_multigpu_gloo.py."""
 import os
@@ -53,6 +54,17 @@ def _worker(rank, world, port, h, w, q):
                             for k in ("rgb", "cls", "final_q", "ic", "hit", "uv", "nsteps"))
         else:
             ok = ok and got0["rgb"] is None and got0["cls"] is None and got0["final_q"] is None
+        # opt-in de-duplicated render: the ranks share the integration of the distinct rays -- every output array must
+        # be the one-ray-per-pixel frame bit for bit (all_gather and root gather), with several times fewer steps integrated
+        for root in (None, 0):
+            dd = render_frame(sc, tex, extras=True, handle=hd, root=root, dedup=True)
+            integrated = hd.last_total_steps()
+            if root is None or rank == 0:
+                ok = ok and all(np.array_equal(np.ascontiguousarray(dd[k]).view(np.uint8), np.ascontiguousarray(got[k]).view(np.uint8))
+                                for k in ("rgb", "cls", "final_q", "ic", "hit", "uv", "nsteps"))
+            else:
+                ok = ok and dd["rgb"] is None
+            ok = ok and 0 < integrated < int(got["nsteps"].astype(np.int64).sum()) // (2 * world) if got["nsteps"] is not None else ok
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

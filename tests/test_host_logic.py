@@ -93,8 +93,12 @@ def test_run_manual_simulation_quirks_without_gpu(tmp_path, monkeypatch):
     bh = BlackHole(1.0); ob = Observer(np.array([30, 0, 0]), np.radians(80), (6, 8))
     img = run_manual_simulation(bh, ob, steps=10, delta=0.1, use_cuda=True, boundary_radius=31, n_samples=0)
     assert img.shape == (6, 8, 3) and img.dtype == np.uint8 and not img.any()
-    with pytest.raises(RuntimeError):
+    # without use_cuda the reference integrates nothing: NameError at raytracing.py:131 when trajectories are sampled,
+    # the black frame + "Summary counts not available" otherwise (raytracing.py:301-314)
+    with pytest.raises(NameError):
         run_manual_simulation(bh, ob, steps=10, delta=0.1, use_cuda=False, boundary_radius=31, n_samples=2)
+    img = run_manual_simulation(bh, ob, steps=10, delta=0.1, use_cuda=False, n_samples=0)
+    assert img.shape == (6, 8, 3) and not img.any()
 
 
 def test_dedup_flag_reaches_the_render_call(tmp_path, monkeypatch):

@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""FP64-pipe instructions per loop body of the render kernel, counted in the SASS of the built library (no GPU).
+
+    python tools/loop_body_fp64.py [--lib <libschw_b200.so>] [--out <json>]
+
+`nvdisasm -gi` prints, for every instruction, the chain of inlined call sites it belongs to.  The instructions of one
+loop body of `persistent_rays<RenderJob, true, true>` are those whose chain passes through the kernel's call of
+`step_BCBA_planar` (schw_kernels.cu); inside it they are split by the call site in `step_BCBA_planar` (schw_device.cuh)
+they were inlined from: the planar tails (`flow_tail_planar`, `mix_planar`) run only on the fast path, the general tails
+(`flow_tail`, `memo_refresh`, the theta `mix`) only off it, everything else on both.  bench.py multiplies these counts by
+the loop bodies the device counted (Counters::warp_iters / planar_iters) to get the FP64-pipe utilisation of a run; the
+JSON is keyed by the SHA of csrc/ so a stale file is detected, and __graft_entry__.build() regenerates it.
+"""
+import argparse
+import collections
+import hashlib
+import json
+import os
+import re
+import subprocess
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "schwarzchild-einsteinpy-raytracing_b200")
+FP64 = ("DFMA", "DMUL", "DADD", "DSETP")
+KERNEL = "persistent_raysINS_9RenderJobELb1ELb1"
+
+
+def csrc_sha():
+    hsh = hashlib.sha256()
+    for f in ("schw_kernels.cu", "schw_device.cuh", "Makefile"):
+        hsh.update(open(os.path.join(PKG, "csrc", f), "rb").read())
+    return hsh.hexdigest()[:16]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lib", default=os.path.join(PKG, "lib", "libschw_b200.so"))
+    ap.add_argument("--out", default=os.path.join(PKG, "lib", "loop_body.json"))
+    a = ap.parse_args()
+    ksrc = open(os.path.join(PKG, "csrc", "schw_kernels.cu")).read().splitlines()
+    dsrc = open(os.path.join(PKG, "csrc", "schw_device.cuh")).read().splitlines()
+    call_lines = [i + 1 for i, l in enumerate(ksrc) if "step_BCBA_planar(" in l and "//" not in l.split("step_BCBA_planar(")[0]]
+    assert len(call_lines) == 1, call_lines
+    call_line = call_lines[0]
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(a.lib)], cwd=d, stdout=subprocess.DEVNULL)
+        cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
+        txt = subprocess.run(["nvdisasm", "-gi", "-c", cubin], cwd=d, capture_output=True, text=True).stdout
+    inside = False
+    chain = []
+    fresh = True            # the next //## line starts a new chain
+    cat_fp = collections.Counter(); cat_all = collections.Counter()
+    for line in txt.splitlines():
+        m = re.match(r"\s*\.section\s+\.text\.(\S+?),", line)
+        if m:
+            inside = KERNEL in m.group(1)
+            continue
+        if not inside:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', line)
+        if m:
+            if fresh:
+                chain = []
+                fresh = False
+            chain.append((os.path.basename(m.group(1)), int(m.group(2))))
+            continue
+        m = re.search(r"^\s+/\*([0-9a-f]+)\*/\s+((?:@!?U?P\d\s+)?)([A-Z0-9_.]+)(.*?);", line)
+        if not m:
+            continue
+        fresh = True
+        if ("schw_kernels.cu", call_line) not in chain:
+            continue
+        # the call site inside step_BCBA_planar = the chain entry right below the kernel's call
+        k = chain.index(("schw_kernels.cu", call_line))
+        site = chain[k - 1] if k > 0 else None
+        text = dsrc[site[1] - 1] if site and site[0] == "schw_device.cuh" else ""
+        deeper = " ".join(dsrc[c[1] - 1] for c in chain[:k] if c[0] == "schw_device.cuh")
+        if "trig_factors(" in deeper or "sincos_flow(" in deeper or "m.hcis = hh * cis" in deeper:
+            cat = "memo_miss"          # re-evaluation of a memoised trig factor: only when an angle's bits changed
+        elif "flow_tail_planar(" in text or "mix_planar(" in text:
+            cat = "fast_only"
+        elif "flow_tail(" in text or "memo_refresh(" in text or re.search(r"if \(!v\d\) mix\(", text) or "++n_general" in text:
+            cat = "general_only"
+        else:
+            cat = "common"
+        op = m.group(3).split(".")[0]
+        cat_all[cat] += 1
+        if op in FP64:
+            cat_fp[cat] += 1
+    assert cat_fp["common"] > 0, "no instruction of the loop body found: did the kernel or the step function change its name?"
+    out = {
+        "csrc_sha": csrc_sha(), "kernel": KERNEL,
+        "fp64_per_body_fast_path": cat_fp["common"] + cat_fp["fast_only"],
+        "fp64_per_body_general": cat_fp["common"] + cat_fp["general_only"],
+        "fp64_per_memo_miss_all_three_flows": cat_fp["memo_miss"],
+        "detail": {"fp64": dict(cat_fp), "static_instructions": dict(cat_all)},
+        "how": "nvdisasm -gi of the built library: instructions whose inline chain passes through the kernel's call of "
+               "step_BCBA_planar, split by call site (tools/loop_body_fp64.py).  'general' = all three flows and the mixing off "
+               "the fast path with the trig memo hitting; the memo-miss re-evaluation (sincos + reciprocal, only when an angle's "
+               "bits changed) is listed separately and not counted by bench.py.  The loop control outside step_BCBA_planar "
+               "(termination pre-test, counters) holds no FP64-pipe instruction",
+    }
+    json.dump(out, open(a.out, "w"), indent=1)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
