@@ -332,6 +332,7 @@ def main():
     if not args.no_extras:
         try:
             tex_np = tex_host.numpy()
+            os.environ["SCHW_DEDUP_REUSE"] = "0"            # every timed frame plans and integrates again
             if world == 1:
                 ref = hd.render(scene, tex_np)
                 best = 1e30
@@ -345,7 +346,6 @@ def main():
                          "note": "schw_render_dedup: pixels whose camera angle agrees bitwise share one integration; same output "
                                  "bits; kernel time of the whole pipeline (keys, sort, integrate, per-pixel epilogue), texture resident"}
             else:
-                os.environ["SCHW_DEDUP_REUSE"] = "0"        # every timed frame plans and integrates again
                 render_frame(scene, tex_np, handle=hd, root=0, dedup=True)
                 best = 1e30
                 for _ in range(max(2, args.steps)):
@@ -366,6 +366,7 @@ def main():
                                      "to rank 0, D2H; wall time incl. the texture upload, max over ranks, best of the timed frames"}
         except Exception as e:                         # the headline must not depend on the opt-in mode
             dedup = {"error": repr(e)}
+        os.environ.pop("SCHW_DEDUP_REUSE", None)
 
     stats = torch.tensor([dev_ms, e2e_s, float(steps_per_frame_local), kern_ms], dtype=torch.float64, device=dev)
     if world > 1:

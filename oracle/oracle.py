@@ -177,3 +177,61 @@ def flat_render(scene, tex):
     rgb = np.zeros((scene.height, scene.width, 3), np.uint8)
     lib().orc_flat_render(C.byref(scene), _ptr(tex, C.c_uint8), _ptr(rgb, C.c_uint8))
     return rgb
+
+
+# ---- binary128 truth (oracle/schw_oracle_q.c) ---------------------------------------------------------
+_SOQ = os.path.join(_HERE, "_build", "libschw_oracle_q.so")
+_libq = None
+
+
+def libq():
+    global _libq
+    if _libq is None:
+        src = os.path.join(_HERE, "schw_oracle_q.c")
+        if not os.path.exists(_SOQ) or os.path.getmtime(_SOQ) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-s"])
+        L = C.CDLL(_SOQ)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+        L.orcq_integrate_batch.argtypes = [dp, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                           ip, dp, dp, ip, C.c_int]
+        L.orcq_integrate_batch_full.argtypes = [dp, dp, C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                C.c_int, dp, dp, ip, C.c_int]
+        _libq = L
+    return _libq
+
+
+def exact_integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega, force_steps=None, nthreads=0, with_momenta=False):
+    """The stepper in binary128 on the same double inputs, rounded to double on output.  Returns (out_qs, nsteps)
+    [, out_ps].  force_steps: per-ray step counts to take regardless of the termination test."""
+    q0s = np.ascontiguousarray(q0s, np.float64); p0s = np.ascontiguousarray(p0s, np.float64)
+    n = q0s.shape[0]
+    out = np.zeros((n, 4)); ns = np.zeros(n, np.int64)
+    ps = np.zeros((n, 4)) if with_momenta else None
+    fs = None if force_steps is None else np.ascontiguousarray(force_steps, np.int64)
+    libq().orcq_integrate_batch(_dp(q0s), _dp(p0s), n, int(steps), float(delta), float(rs), float(r_max), float(omega),
+                                _ptr(fs, C.c_int64), _dp(out), _dp(ps), _ptr(ns, C.c_int64), int(nthreads))
+    return (out, ns, ps) if with_momenta else (out, ns)
+
+
+def exact_integrate_batch_full(q0s, p0s, steps, delta, rs, r_max, omega, stop=True, nthreads=0, with_momenta=False):
+    """Trajectories (n, steps, 4) in binary128 (rounded to double); stop=False continues past the termination test."""
+    q0s = np.ascontiguousarray(q0s, np.float64); p0s = np.ascontiguousarray(p0s, np.float64)
+    n = q0s.shape[0]
+    traj = np.zeros((n, int(steps), 4)); rows = np.zeros(n, np.int64)
+    mom = np.zeros((n, int(steps), 4)) if with_momenta else None
+    libq().orcq_integrate_batch_full(_dp(q0s), _dp(p0s), n, int(steps), float(delta), float(rs), float(r_max), float(omega),
+                                     int(bool(stop)), _dp(traj), _dp(mom), _ptr(rows, C.c_int64), int(nthreads))
+    return (traj, mom, rows) if with_momenta else (traj, rows)
+
+
+def ulp_ensemble(q0s, p0s, steps, delta, rs, r_max, omega, force_steps=None, eps=2.2e-16):
+    """FP64 evaluations of the reference arithmetic on the inputs and on +-1-ulp (relative eps) perturbations of each
+    component of p0: list of (out_qs, nsteps), unperturbed first.  With force_steps the termination test is replaced
+    by the given per-ray step counts (integrate_batch_full semantics are not needed: final states only)."""
+    p0s = np.ascontiguousarray(p0s, np.float64)
+    runs = [integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega)]
+    for sgn in (1.0, -1.0):
+        for comp in range(4):
+            p = p0s.copy(); p[:, comp] *= (1.0 + sgn * eps)
+            runs.append(integrate_batch(q0s, p, steps, delta, rs, r_max, omega))
+    return runs

@@ -111,7 +111,7 @@ __device__ __forceinline__ void wait_flag_warp(const unsigned *flag, unsigned *e
     const volatile unsigned *f = flag;
     bool seen = false;
     for (int spin = 0; spin < (1 << 22) && !(seen = __any_sync(0xffffffffu, *f != 0u)); ++spin) __nanosleep(512);
-    if (!seen && (threadIdx.x & 31u) == 0u) atomicOr(err, kErrTexWait);
+    if (!seen) atomicOr(err, kErrTexWait);
     __threadfence();
 }
 

@@ -80,3 +80,25 @@ def test_header_cites_reference_interfaces():
     for cite in ("cuda_geodesic.py:639-645", "cuda_geodesic.py:647-653", "raytracing.py:60-88", "utils.py:91-141",
                  "raytracing.py:166-174,181-273", "background.py"):
         assert cite in hdr, cite
+
+
+def test_step_loop_sass_budget():
+    """No GPU needed: the SASS of the built render kernel.  (1) every *_sync vote of the step loop is reached provably
+    convergently -- the compiler emitted no BRA.DIV divergence handling around them (a lane-conditional atomic next to a
+    vote once cost 13 % of the frame time); (2) the loop body holds at most 100 FP64-pipe instructions on the planar fast
+    path and 121 off it (3 flows x 22 / 27 + the mixed flow 34 / 40); (3) the artefact bench.py reads is the one of this
+    source tree."""
+    import json
+    import subprocess
+    import sys
+    import schw_b200
+    schw_b200.build()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "loop_body_fp64.py")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["bra_div_in_kernel"] == 0
+    assert 90 <= d["fp64_per_body_fast_path"] <= 100 and d["fp64_per_body_general"] <= 121
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["csrc_sha"] == bench.csrc_sha()
+    assert json.load(open(os.path.join(ROOT, "schwarzchild-einsteinpy-raytracing_b200", "lib", "loop_body.json")))["csrc_sha"] == d["csrc_sha"]

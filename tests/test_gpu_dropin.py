@@ -166,8 +166,8 @@ def test_cuda_flat_raytrace_wrappers(handle, orc):
         hit = obs + (-b + np.sqrt(b * b - 4 * (d @ d) * c)) / (2 * (d @ d)) * d
         want = obs[None, :] + (np.arange(100) / 99.0)[:, None] * (hit - obs)[None, :]
         assert np.allclose(trajs[s], want, rtol=0, atol=1e-12)
-    # a ray that misses the sphere (observer outside it, pointing away): black pixel, zero trajectory rows
-    miss, tr = cuda_flat_raytrace_with_trajectories(np.array([50.0, 0, 0]), np.array([[1.0, 0, 0]]), 10.0, *patch, tex, [0], n_points=5)
+    # a ray whose line misses the sphere (observer outside it, looking sideways): black pixel, zero trajectory rows
+    miss, tr = cuda_flat_raytrace_with_trajectories(np.array([50.0, 0, 0]), np.array([[0.0, 1.0, 0]]), 10.0, *patch, tex, [0], n_points=5)
     assert not miss.any() and not tr.any()
 
 

@@ -7,28 +7,20 @@ Bars (north_star / SURVEY §8c):
     stated bands — G: |b/(3 sqrt3 M) - 1| < 1e-3 (grazing), H: trajectory reaches r < 2.5 (horizon
     blow-up, rounding-chaotic in the reference itself) — and texels whose continuous coordinate sits
     within 1e-6 of a rounding boundary;
-  * final photon positions: 1e-9 relative (FP64) outside the bands;
-  * single-ray trajectories: 1e-9 relative per stored step.
+  * final photon positions and single-ray trajectories: within 1e-9 relative of the EXACT result of the discrete map
+    (the stepper in binary128, oracle/schw_oracle_q.c) wherever the reference's own FP64 arithmetic is that accurate;
+    where it is not (exponentially unstable omega = 0.01 trajectories, horizon blow-ups), at most 4x as far from the
+    truth as the reference's FP64 ensemble (its result on the inputs and on 1-ulp perturbations of them) -- see
+    helpers.truth_bound.  No tolerance here is looser than 1e-9 without that measured backing.
 """
 import numpy as np
 import pytest
 
 from conftest import relerr
-from helpers import (STATE_RTOL, in_band_g, near_rounding_boundary, random_rays, scene_kwargs_from_cfg,
-                     state_close, synthetic_sky, texel_coords)
+from helpers import (STATE_RTOL, assert_final_states, final_state_vs_truth, in_band_g, near_rounding_boundary, random_rays, scene_kwargs_from_cfg,
+                     state_close, synthetic_sky, texel_coords, trajectory_vs_truth, truth_bound)
 
 pytestmark = pytest.mark.gpu
-
-
-COND_MAX = 1e-11     # rays whose REFERENCE result moves by more than this under a 1-ulp input change are ill-conditioned
-
-
-def _well_posed(orc, q0s, p0s, steps, delta, rs, r_max, omega):
-    """Rays on which the 1e-9 state bar applies: outside band G (grazing), outside band H (closest approach
-    of either phase-space copy >= 2.5, oracle bookkeeping) and well-conditioned in the reference's own arithmetic."""
-    _, _, rmin = orc.integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega, want_rmin=True)
-    cond = orc.conditioning(q0s, p0s, steps, delta, rs, r_max, omega)
-    return ~in_band_g(p0s) & (rmin >= 2.5) & (cond <= COND_MAX)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -38,37 +30,33 @@ def test_integrate_batch_default_scene_vs_reference_golden(handle, orc, golden):
     g = golden("stepper_default.npz")
     steps, delta, r_max, omega = int(g["steps"]), float(g["delta"]), float(g["r_max"]), float(g["omega"])
     out, ns = handle.integrate_batch(g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega, want_steps=True)
-    _, ns_ref = orc.integrate_batch(g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega)
-    ok = _well_posed(orc, g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega)
-    assert ok.sum() >= 17
-    assert np.array_equal(ns[ok], ns_ref[ok])                                  # same termination step
-    assert state_close(out[ok], g["out_qs"][ok]).all(), relerr(out[ok], g["out_qs"][ok], 1.0).max()
-    # band-H rays: captured/escaped side must still agree in the render (alpha0 mask), not asserted here
+    r = assert_final_states(orc, out, ns, g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega, "default-scene golden", 0.6, max_unstable=0.25)
+    # and directly against what the reference itself produced, where the 1e-9 bar applies
+    assert state_close(out[r["tight"]], g["out_qs"][r["tight"]], 2e-9).all()
 
 
 def test_integrate_batch_general_rays_vs_reference_golden(handle, orc, golden):
     g = golden("stepper_general.npz")
     steps, delta, r_max = int(g["steps"]), float(g["delta"]), float(g["r_max"])
     for tag, omega in (("out_w1", 1.0), ("out_w001", 0.01)):
-        out = handle.integrate_batch(g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega)
-        ok = _well_posed(orc, g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega)
-        assert ok.sum() > 80, ok.sum()
-        assert state_close(out[ok], g[tag][ok]).all(), (tag, relerr(out[ok], g[tag][ok], 1.0).max())
+        out, ns = handle.integrate_batch(g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega, want_steps=True)
+        r = assert_final_states(orc, out, ns, g["q0s"], g["p0s"], steps, delta, 2.0, r_max, omega, f"general golden {tag}", 0.5)
+        assert state_close(out[r["tight"]], g[tag][r["tight"]], 2e-9).all(), tag
 
 
-def test_integrate_batch_random_rays_vs_oracle(handle, orc):
+def test_integrate_batch_random_rays_vs_truth(handle, orc):
     q0s, p0s = random_rays(4096, seed=11)
     steps, delta, rs, r_max, omega = 4000, 0.02, 2.0, 45.0, 1.0
     out, ns = handle.integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega, want_steps=True)
     ref, ns_ref = orc.integrate_batch(q0s, p0s, steps, delta, rs, r_max, omega)
-    ok = _well_posed(orc, q0s, p0s, steps, delta, rs, r_max, omega)
-    assert ok.sum() > 2000, ok.sum()
-    assert np.array_equal(ns[ok], ns_ref[ok])
-    assert state_close(out[ok], ref[ok]).all(), relerr(out[ok], ref[ok], 1.0).max()
+    assert_final_states(orc, out, ns, q0s, p0s, steps, delta, rs, r_max, omega, "4096 random rays", 0.6)
     # captured/escaped side agrees for every ray outside the grazing band, ill-conditioned or not
     side = lambda r: np.where(r <= 1.1 * rs, 0, np.where(r >= r_max, 1, 2))
     far = np.abs(np.abs(p0s[:, 3] / p0s[:, 0]) / (3 * np.sqrt(3)) - 1) > 0.05
     assert np.mean(side(out[far, 1]) == side(ref[far, 1])) > 0.995
+    # the weakly coupled integrator (omega = 0.01, the single-ray script's setting) on the same rays
+    out, ns = handle.integrate_batch(q0s[:1024], p0s[:1024], steps, delta, rs, r_max, 0.01, want_steps=True)
+    assert_final_states(orc, out, ns, q0s[:1024], p0s[:1024], steps, delta, rs, r_max, 0.01, "1024 random rays, omega 0.01", 0.9)
 
 
 def test_integrate_batch_edge_cases(handle, orc):
@@ -104,13 +92,15 @@ def test_single_ray_trajectory_k3(handle, golden):
     n = k["traj"].shape[0]
     assert rows[0] == n == 6665
     assert abs(int(rows[0]) - n) <= 2 and n == 6665
-    # This omega=0.01 trajectory is exponentially unstable in the reference's own arithmetic: a 1-ulp change
-    # of p0 moves the reference's state by 2e-12 at step 3000, 8e-9 at 5000, 3e-7 at 6600 and 4e-6 at 6660
-    # (tests/test_oracle_golden.py::test_k3_conditioning).  Per-step bar: 1e-9 while the conditioning allows
-    # it, then 1000x the measured 1-ulp sensitivity.
-    assert state_close(traj[0, :2500], k["traj"][:2500]).all(), relerr(traj[0, :2500], k["traj"][:2500], 1.0).max()
-    assert state_close(traj[0, 2500:4500], k["traj"][2500:4500], 1e-7).all()
-    assert state_close(traj[0, 4500:6600], k["traj"][4500:6600], 1e-3).all()
+    # This omega=0.01 trajectory is exponentially unstable: against the binary128 truth the REFERENCE's own FP64 rows are
+    # off by 5e-12 at step 2500, 1.6e-8 at 4500, 4e-6 at 6600 (tests/test_oracle_golden.py::test_k3_reference_error_vs_truth).
+    # Per-row bar: |ours - exact| <= max(1e-9, 4 x the envelope of the nine-member FP64 ensemble and the golden itself).
+    t = trajectory_vs_truth(orc, traj[0], n - 1, k["q0"], k["p0"], int(k["steps"]), float(k["delta"]), 2.0, float(k["r_max"]),
+                            float(k["omega"]), extra_refs=[k["traj"][:n - 1]])
+    assert t["ok"].all(), (np.argwhere(~t["ok"])[:5], (t["err"] / t["bound"]).max())
+    rel = (t["bound"] / np.maximum(np.abs(t["exact"]), 1.0)).max(1)
+    assert rel[:3000].max() <= STATE_RTOL * (1 + 1e-12)                          # the 1e-9 bar itself over the first 3000 rows
+    assert state_close(traj[0, :2000], k["traj"][:2000]).all()                   # and directly against the reference's rows there
     assert not traj[0, rows[0]:].any()                 # zero rows after termination
 
 
@@ -121,19 +111,37 @@ def test_trajectories_vs_einsteinpy_kats(handle, golden):
     traj = handle.integrate_batch_full(q0[None], p0[None], 2900, float(k["delta"]), 2.0, 1e6, float(k["omega"]))
     T = traj[0][k["step"]]
     xyz = np.stack([T[:, 1] * np.cos(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.sin(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.cos(T[:, 2])], 1)
-    # K1 (omega = 0.01) is exponentially unstable in the reference arithmetic itself: a 1-ulp change of p0 moves
-    # the oracle's state by 1.5e-13 at step 1500, 4e-12 at 2000 and 9e-9 at 2500 (the ray then turns around at
-    # r = 112 and blows up).  1e-9 where the conditioning allows it, 1e-6 up to step 2400.
-    for lo, hi, tol in ((0, 1500, 1e-9), (1500, 2400, 1e-6)):
-        sel = (k["step"] >= lo) & (k["step"] < hi)
-        assert relerr(T[sel, 0], k["vals"][sel, 0]).max() < tol
-        assert (np.abs(xyz[sel] - k["vals"][sel, 1:4]) <= tol * np.maximum(np.abs(k["vals"][sel, 1:4]), 1.0)).all()
+    # K1 (omega = 0.01) is exponentially unstable in FP64: bar per stored row = max(1e-9, 4 x envelope) against the
+    # binary128 truth, in the golden's own Cartesian coordinates; EinsteinPy's output is one more member of the envelope.
+    def cart(T):
+        return np.stack([T[:, 0], T[:, 1] * np.cos(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.sin(T[:, 3]) * np.sin(T[:, 2]),
+                         T[:, 1] * np.cos(T[:, 2])], 1)
+
+    def check(q0, p0, nrows, delta, omega, steps_idx, gold_cart, traj):
+        exact, _ = orc.exact_integrate_batch_full(q0[None], p0[None], nrows, delta, 2.0, 1e6, omega, stop=False)
+        refs = [gold_cart]
+        for sgn in (0.0, 1.0, -1.0):
+            for comp in range(4 if sgn else 1):
+                p = p0.copy(); p[comp] *= (1.0 + sgn * 2.2e-16)
+                refs.append(cart(orc.integrate_batch_full(q0[None], p[None], nrows, delta, 2.0, 1e300, omega)[0][0][steps_idx]))
+        E = cart(exact[0][steps_idx])
+        bound, env = truth_bound(E, refs)
+        err = np.abs(cart(traj[steps_idx]) - E)
+        assert (err <= bound).all(), (np.argwhere(err > bound)[:5], (err / bound).max())
+        return bound / np.maximum(np.abs(E), 1.0)
+
+    sel = k["step"] < 2400
+    rel = check(q0, p0, 2900, float(k["delta"]), float(k["omega"]), k["step"][sel], k["vals"][sel, 0:4], traj[0])
+    assert rel[k["step"][sel] < 1200].max() <= STATE_RTOL * (1 + 1e-12)
     k2 = golden("kat_k2_einsteinpy_notebook.npz")
     q0 = k2["q0"]; p0 = np.array([_null_pt(q0, k2["p_sph"]), *k2["p_sph"]])
     traj = handle.integrate_batch_full(q0[None], p0[None], 10001, float(k2["delta"]), 2.0, 1e6, float(k2["omega"]))
     T = traj[0][k2["step"]]
     xyz = np.stack([T[:, 1] * np.cos(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.sin(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.cos(T[:, 2])], 1)
     assert (np.abs(xyz - k2["xyz"]) <= 1e-9 * np.maximum(np.abs(k2["xyz"]), 1.0)).all()
+    gold = np.concatenate([np.full((len(k2["step"]), 1), np.nan), k2["xyz"]], 1)         # (the notebook holds positions only)
+    rel = check(q0, p0, 10001, float(k2["delta"]), float(k2["omega"]), k2["step"], gold, traj[0])
+    assert rel.max() <= STATE_RTOL * (1 + 1e-12)                                       # K2 is stable: the 1e-9 bar on every row
 
 
 def test_integrate_batch_full_many_rays_vs_oracle(handle, orc):
@@ -141,12 +149,16 @@ def test_integrate_batch_full_many_rays_vs_oracle(handle, orc):
     steps, delta, rs, r_max, omega = 600, 0.1, 2.0, 45.0, 1.0
     traj, rows = handle.integrate_batch_full(q0s, p0s, steps, delta, rs, r_max, omega, want_rows=True)
     ref, rows_ref = orc.integrate_batch_full(q0s, p0s, steps, delta, rs, r_max, omega)
-    ok = _well_posed(orc, q0s, p0s, steps, delta, rs, r_max, omega)
-    assert ok.sum() > 30, ok.sum()
-    assert np.array_equal(rows[ok], rows_ref[ok])
-    assert state_close(traj[ok], ref[ok]).all()
-    for k in np.nonzero(ok)[0]:
+    n_tight = 0
+    for k in range(len(q0s)):
+        t = trajectory_vs_truth(orc, traj[k], rows[k], q0s[k], p0s[k], steps, delta, rs, r_max, omega)
+        assert t["ok"].all(), (k, (t["err"] / t["bound"]).max())
+        tight = (t["bound"] <= STATE_RTOL * np.maximum(np.abs(t["exact"]), 1.0) * (1 + 1e-12)).all()
+        n_tight += tight
+        if tight:
+            assert rows[k] == rows_ref[k]
         assert not traj[k, rows[k]:].any()
+    assert n_tight > 35, n_tight                      # the 1e-9 bar itself on most rays; the others blow up near the horizon
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -411,19 +423,31 @@ def test_render_other_scenes_vs_oracle(handle, orc, kw):
     full = dict(patch_center_theta=np.pi / 2, patch_center_phi=np.pi, patch_size_theta=np.pi, patch_size_phi=2 * np.pi,
                 flip_theta=False, flip_phi=False)
     full.update(kw)
-    # rays whose reference result is ill-conditioned may legitimately change class; everything else is bit-exact
+    # Every ray is held to a bar.  A ray may change class only if FP64 itself cannot decide it: some member of the
+    # reference's nine-member 1-ulp ensemble ends on another side of a class threshold or after another number of steps.
     sc = orc.make_scene(**kw)
     q0 = np.tile(np.array([0.0, np.hypot(*kw["obs"][:2]), np.pi / 2, 0.0]), (h * w, 1))
-    cond = orc.conditioning(q0, ref["ic"][:, :4].copy(), sc.steps, sc.delta, 2 * sc.mass, sc.r_max, sc.omega)
-    ok = (cond <= COND_MAX) & ~in_band_g(ref["ic"][:, :4], mass=sc.mass)
-    assert ok.mean() > 0.6
+    p0 = ref["ic"][:, :4].copy()
+    rs = 2 * sc.mass
+    ens = orc.ulp_ensemble(q0, p0, sc.steps, sc.delta, rs, sc.r_max, sc.omega)
+    side = lambda r: np.where(r <= 1.2 * rs, 0, np.where(r >= 100.0, 1, np.where(r >= sc.r_max, 2, 4)))      # raytracing.py:210-216
+    decided = np.ones(h * w, bool)
+    for o, n_k in ens:
+        with np.errstate(invalid="ignore"):
+            decided &= (side(o[:, 1]) == side(ens[0][0][:, 1])) & (n_k == ens[0][1])
     masked = ref["cls"].reshape(-1) == 0                        # forced to 'bh' by the analytic mask whatever the integrator did
-    good = ok | masked
+    good = decided | masked
+    _, _, rmin = orc.integrate_batch(q0, p0, sc.steps, sc.delta, rs, sc.r_max, sc.omega, want_rmin=True)
+    und = ~good
+    print(f"undecidable in FP64: {und.mean():.4f} of {h * w} rays")
+    assert und.mean() <= 0.02
+    assert (in_band_g(p0, mass=sc.mass) | (rmin < 2.5 * sc.mass))[und].all()          # each is in a stated band (G or H)
     assert np.array_equal(got["cls"].reshape(-1)[good], ref["cls"].reshape(-1)[good])
     assert (got["cls"].reshape(-1) != ref["cls"].reshape(-1)).mean() < 0.01
     fu, fv = texel_coords(full, ref["hit"][:, 0], ref["hit"][:, 1])
     diff = np.any(got["rgb"].reshape(-1, 3) != ref["rgb"].reshape(-1, 3), axis=1) & good
     assert np.all(near_rounding_boundary(fu, fv)[diff])
-    sel = ok & ~masked
+    sel = decided & ~masked
     assert np.array_equal(got["nsteps"][sel], ref["nsteps"][sel])
-    assert state_close(got["final_q"][sel], ref["final_q"][sel]).all(), relerr(got["final_q"][sel], ref["final_q"][sel], 1.0).max()
+    assert_final_states(orc, got["final_q"][sel], got["nsteps"][sel].astype(np.int64), q0[sel], p0[sel], sc.steps, sc.delta, rs,
+                         sc.r_max, sc.omega, "render", 0.5)

@@ -154,6 +154,48 @@ def test_k3_conditioning(orc, golden):
     assert 1e-9 < d[6000:6600].max() < 1e-5
 
 
+def test_k3_reference_error_vs_truth(orc, golden):
+    """The binary128 truth (oracle/schw_oracle_q.c) on config 2: how far the REFERENCE's own FP64 rows are from the
+    exact result of the discrete map -- the measured backing of every tolerance above 1e-9 in the GPU tests."""
+    k = golden("single_ray_k3.npz")
+    n = k["traj"].shape[0]
+    exact, rows = orc.exact_integrate_batch_full(k["q0"][None], k["p0"][None], n, float(k["delta"]), 2.0, float(k["r_max"]),
+                                                 float(k["omega"]), stop=False)
+    err = (np.abs(k["traj"] - exact[0]) / np.maximum(np.abs(exact[0]), 1.0)).max(1)
+    assert err[:2000].max() < 1e-11 and err[:3000].max() < 2.5e-10               # the reference is 1e-9-accurate up to ~row 3000
+    assert 1e-9 < err[4500] < 1e-7 and 1e-7 < err[6600] < 1e-4                   # and loses six more digits by the end
+    # with the termination test the exact trajectory stops within a row or two of the reference's 6665 rows
+    _, rows_stop = orc.exact_integrate_batch_full(k["q0"][None], k["p0"][None], n + 50, float(k["delta"]), 2.0, float(k["r_max"]),
+                                                  float(k["omega"]))
+    assert abs(int(rows_stop[0]) - n) <= 3
+
+
+def test_truth_oracle_is_pinned_by_the_einsteinpy_kats(orc, golden):
+    """The binary128 stepper is the same map as EinsteinPy's FANTASY order 2: on the stable K2 trajectory (10 000 steps) and
+    on the first 1200 rows of K1 it agrees with the genuine EinsteinPy outputs to FP64 rounding (they are FP64 results)."""
+    k2 = golden("kat_k2_einsteinpy_notebook.npz")
+    q0 = k2["q0"]; p0 = np.array([_null_pt(q0, k2["p_sph"]), *k2["p_sph"]])
+    T, _ = orc.exact_integrate_batch_full(q0[None], p0[None], 10001, float(k2["delta"]), 2.0, 1e6, float(k2["omega"]), stop=False)
+    T = T[0][k2["step"]]
+    xyz = np.stack([T[:, 1] * np.cos(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.sin(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.cos(T[:, 2])], 1)
+    assert relerr(xyz, k2["xyz"], 1.0).max() < 1e-10           # measured 5e-12: FP64 rounding accumulated over 10 000 steps
+    k = golden("kat_k1_einsteinpy_trajectory.npz")
+    q0 = k["q0"]; p0 = np.array([_null_pt(q0, k["p_sph"]), *k["p_sph"]])
+    T, M, _ = orc.exact_integrate_batch_full(q0[None], p0[None], 2900, float(k["delta"]), 2.0, 1e6, float(k["omega"]), stop=False,
+                                             with_momenta=True)
+    sel = k["step"] < 1200
+    T, M = T[0][k["step"][sel]], M[0][k["step"][sel]]
+    mine = np.stack([T[:, 0], T[:, 1] * np.cos(T[:, 3]) * np.sin(T[:, 2]), T[:, 1] * np.sin(T[:, 3]) * np.sin(T[:, 2]),
+                     T[:, 1] * np.cos(T[:, 2]), M[:, 0], M[:, 1], M[:, 2], M[:, 3]], 1)
+    assert relerr(mine, k["vals"][sel], 1.0).max() < 1e-10
+    # and with the double oracle on well-conditioned rays to a few ulps times the step count
+    from helpers import random_rays
+    q0s, p0s = random_rays(64, seed=2)
+    a, na = orc.integrate_batch(q0s, p0s, 300, 0.05, 2.0, 1e6, 1.0)
+    b, nb = orc.exact_integrate_batch(q0s, p0s, 300, 0.05, 2.0, 1e6, 1.0, force_steps=na)
+    assert np.median(relerr(a, b, 1.0).max(1)) < 1e-13
+
+
 def test_flat_render_vs_reference(orc, golden):
     """N1: save_no_gravity_image_with_background (background.py:19-141).  F1 is the main.py default, which the
     reference renders all black (phi0 % 2pi == phi1 % 2pi == 0 for a 360-degree patch, background.py:8-17)."""

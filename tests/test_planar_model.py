@@ -178,3 +178,21 @@ def test_random_parameter_sets_and_near_threshold_rays(model):
     assert n_rays == 720 and n_steps > 100000
     assert 0.1 * n_steps < n_planar_steps < 0.95 * n_steps         # both paths are exercised ...
     assert n_mixed > 30                                            # ... also within one ray
+
+
+def test_device_arithmetic_meets_the_truth_bar_on_the_cpu(model, orc):
+    """The kernels' own arithmetic (this header compiled for the host: same FMAs, same reciprocal refinement, same sincos;
+    only the 2^-20 hardware reciprocal seed is emulated) against the binary128 truth, with the bar of the GPU parity tests
+    (helpers.assert_final_states): a re-derivation of the flows that lost accuracy would fail here, without a GPU."""
+    from helpers import assert_final_states, random_rays
+    params, run = model
+    steps, delta, rs, r_max = 4000, 0.02, 2.0, 45.0
+    for omega, n, min_tight in ((1.0, 384, 0.6), (0.01, 192, 0.9)):
+        q0s, p0s = random_rays(n, seed=31)
+        buf = params(steps, delta, rs, r_max, omega)
+        out = np.zeros((n, 4)); ns = np.zeros(n, np.int64)
+        for i in range(n):
+            r = run(buf, q0s[i], p0s[i])
+            out[i] = r["fp"]; ns[i] = r["steps"]
+            assert r["first_diff"] == -1 and r["same_end"]
+        assert_final_states(orc, out, ns, q0s, p0s, steps, delta, rs, r_max, omega, f"host model, omega {omega}", min_tight)

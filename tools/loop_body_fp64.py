@@ -51,6 +51,7 @@ def main():
     chain = []
     fresh = True            # the next //## line starts a new chain
     cat_fp = collections.Counter(); cat_all = collections.Counter()
+    bra_div = 0
     for line in txt.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", line)
         if m:
@@ -69,6 +70,7 @@ def main():
         if not m:
             continue
         fresh = True
+        bra_div += m.group(3).startswith("BRA.DIV")
         if ("schw_kernels.cu", call_line) not in chain:
             continue
         # the call site inside step_BCBA_planar = the chain entry right below the kernel's call
@@ -94,6 +96,9 @@ def main():
         "fp64_per_body_fast_path": cat_fp["common"] + cat_fp["fast_only"],
         "fp64_per_body_general": cat_fp["common"] + cat_fp["general_only"],
         "fp64_per_memo_miss_all_three_flows": cat_fp["memo_miss"],
+        # BRA.DIV = the compiler could not prove that a *_sync vote is reached convergently and emitted divergence handling
+        # around it (a 13 % slowdown of the step loop when it happened); must stay 0 (tests/test_host_logic.py)
+        "bra_div_in_kernel": bra_div,
         "detail": {"fp64": dict(cat_fp), "static_instructions": dict(cat_all)},
         "how": "nvdisasm -gi of the built library: instructions whose inline chain passes through the kernel's call of "
                "step_BCBA_planar, split by call site (tools/loop_body_fp64.py).  'general' = all three flows and the mixing off "
