@@ -300,7 +300,9 @@ def main():
     step_e2e()
     barrier()
     t0 = time.perf_counter()
+    frame0 = None
     for _ in range(args.steps):
+        frame0 = None                   # (drop the previous frame first: its page-locked arrays go back to the pool)
         frame0 = step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0

@@ -117,6 +117,13 @@ int  schw_integrate_batch_full(schw_handle *h, const double *q0s, const double *
                                int64_t steps, double delta, double rs, double r_max, double omega,
                                double *out_traj, int64_t *out_rows);
 
+/* Device-resident variant for trajectory dumps at scale: (n,steps,4) f64 in HBM, 32 B per step per ray,
+ * written as full 128-byte lines.  zero_fill != 0 clears the buffer first (the reference's np.zeros, :649); otherwise rows
+ * after a ray's last stored row are left untouched.  d_out_rows: (n,) i64 or NULL.  Enqueue only. */
+int  schw_integrate_batch_full_dev(schw_handle *h, const double *d_q0s, const double *d_p0s, int64_t n,
+                                   int64_t steps, double delta, double rs, double r_max, double omega,
+                                   double *d_out_traj, int64_t *d_out_rows, int zero_fill, void *cuda_stream);
+
 /* Decimated variant: same integration, but only the rows whose step index is listed in the strictly
  * ascending row_idx[0..nidx) are produced, out: (n,nidx,4) f64 (zero where the ray ended earlier).  With
  * row_idx = np.linspace(0, steps-1, min(1000, steps), dtype=int32) this is exactly what the reference keeps of
@@ -248,6 +255,12 @@ int  schw_fp64_peak_probe(schw_handle *h, double *tflops, float *ms);
  * fast_rcp, sincos_flow — the replacements for the reference's `/` and np.sin/np.cos inside
  * simulation/cuda_geodesic.py:433-474) on n host values, for accuracy tests. */
 int  schw_math_probe(schw_handle *h, const double *x, int64_t n, double *rcp, double *sn, double *cs);
+
+/* Diagnostic / measurement: the loop body of the render kernel alone (no queue, refill or epilogue) on camera-like rays,
+ * variant = 100 * rays per thread + resident CTAs per SM requested (106, 105, 104, 204, 203, 202): kernel time and
+ * warp-steps executed, from which SM cycles per warp-step follow. */
+int  schw_step_probe(schw_handle *h, int variant, int iters, double delta, float *ms, uint64_t *warp_steps,
+                     int *ctas_per_sm, int *regs);
 
 /* Diagnostic, needs no device: the step parameters exactly as the kernels receive them (csrc/schw_device.cuh:
  * StepParams, incl. the thresholds of the planar fast path), for the host-compiled model of the step loop in

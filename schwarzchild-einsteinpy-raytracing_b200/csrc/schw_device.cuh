@@ -403,6 +403,96 @@ __device__ __forceinline__ void step_BCBA_planar(RayState &S, const StepParams &
     next = v4 & (hi_abs(S.p1h) < T) & (__double2hiint(S.q2r) >= RT) & (hi_abs(S.p1p) >= pp_hi);
 }
 
+// The same loop body for R rays per thread (R independent geodesics interleaved in one instruction stream): every vote
+// covers the R rays of all 32 lanes, so the loop control, the votes, the branches and the constant loads are paid once
+// per R ray-steps, and the R dependency chains hide each other's FP64 latency.  R = 1 is step_BCBA_planar itself.
+template <int R>
+__device__ __forceinline__ void step_BCBA_planar_n(RayState (&S)[R], const StepParams &P, Memo2 *M /*[R], stride mstride*/,
+                                                   int mstride, const int (&pp_hi)[R], int &tok, bool &next, int &n_general)
+{
+    constexpr unsigned kFullMask = 0xffffffffu;
+    const int T = P.pl_ph_hi, RT = P.pl_r_hi;
+    if (!tok) {
+        bool c = true;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            c &= is_th_eq(S[r].q1h) & is_th_eq(S[r].q2h) & (hi_abs(S[r].p1h) < T) & (__double2hiint(S[r].q2r) >= RT) &
+                 (hi_abs(S[r].p1p) >= pp_hi[r]);
+        tok = __all_sync(kFullMask, c);
+    }
+    const bool v1 = tok != 0;
+    FlowHead f[R];
+    // ---- B(d/2) ----
+#pragma unroll
+    for (int r = 0; r < R; ++r) f[r] = flow_head(S[r].q2r, S[r].p1t, S[r].p1r, S[r].q1t, S[r].q1r, P.h, P.h_rs, P.rs);
+    if (!v1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            Memo2 &m = M[r * mstride];
+            memo_refresh(S[r].q2h, P.h, m.m2);
+            flow_tail(f[r], S[r].p1h, S[r].p1p, m.m2.is, m.m2.hcis, S[r].p2r, S[r].p2h, S[r].q1h, S[r].q1p, P.h);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) flow_tail_planar(f[r], S[r].p1p, P.pl_hcB, S[r].p2r, S[r].p2h, S[r].q1p, P.h);
+    }
+    // ---- C(d) ----
+    bool c2 = v1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        mix(S[r].q1r, S[r].p1r, S[r].q2r, S[r].p2r, P.mg, P.mhs);
+        mix(S[r].q1p, S[r].p1p, S[r].q2p, S[r].p2p, P.mg, P.mhs);
+        c2 &= (hi_abs(S[r].p2h) < T) & (__double2hiint(S[r].q2r) >= RT) & (hi_abs(S[r].p1p) >= pp_hi[r]);
+    }
+    const bool v2 = __all_sync(kFullMask, c2);
+#pragma unroll
+    for (int r = 0; r < R; ++r) mix(S[r].q1t, S[r].p1t, S[r].q2t, S[r].p2t, P.mg, P.mhs);
+    if (!v2) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) mix(S[r].q1h, S[r].p1h, S[r].q2h, S[r].p2h, P.mg, P.mhs);
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) mix_planar(S[r].p1h, S[r].p2h, P.mg, P.pl_zero_hs);
+    }
+    // ---- B(d/2) ----
+#pragma unroll
+    for (int r = 0; r < R; ++r) f[r] = flow_head(S[r].q2r, S[r].p1t, S[r].p1r, S[r].q1t, S[r].q1r, P.h, P.h_rs, P.rs);
+    if (!v2) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            Memo2 &m = M[r * mstride];
+            memo_refresh(S[r].q2h, P.h, m.m2);
+            flow_tail(f[r], S[r].p1h, S[r].p1p, m.m2.is, m.m2.hcis, S[r].p2r, S[r].p2h, S[r].q1h, S[r].q1p, P.h);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) flow_tail_planar(f[r], S[r].p1p, P.pl_hcB, S[r].p2r, S[r].p2h, S[r].q1p, P.h);
+    }
+    // ---- A(d) ----
+    bool c4 = v2;
+#pragma unroll
+    for (int r = 0; r < R; ++r) c4 &= (hi_abs(S[r].p2h) < T) & (__double2hiint(S[r].q1r) >= RT) & (hi_abs(S[r].p2p) >= pp_hi[r]);
+    const bool v4 = __all_sync(kFullMask, c4);
+#pragma unroll
+    for (int r = 0; r < R; ++r) f[r] = flow_head(S[r].q1r, S[r].p2t, S[r].p2r, S[r].q2t, S[r].q2r, P.delta, P.d_rs, P.rs);
+    if (!v4) {
+        ++n_general;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            Memo2 &m = M[r * mstride];
+            memo_refresh(S[r].q1h, P.delta, m.m1);
+            flow_tail(f[r], S[r].p2h, S[r].p2p, m.m1.is, m.m1.hcis, S[r].p1r, S[r].p1h, S[r].q2h, S[r].q2p, P.delta);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) flow_tail_planar(f[r], S[r].p2p, P.pl_hcA, S[r].p1r, S[r].p1h, S[r].q2p, P.delta);
+    }
+    bool nx = v4;
+#pragma unroll
+    for (int r = 0; r < R; ++r) nx &= (hi_abs(S[r].p1h) < T) & (__double2hiint(S[r].q2r) >= RT) & (hi_abs(S[r].p1p) >= pp_hi[r]);
+    next = nx;
+}
+
 // B(d/2) C(d) B(d/2): the part of _fantasy_step_ord2 (cuda_geodesic.py:569-575) between the two
 // A half-flows.  After it q1 is final for this step (the trailing A does not touch q1), so the
 // termination test may equally be made after the merged A(d) that follows.

@@ -351,47 +351,105 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
 
 // ---------------------------------------------------------------------------------------------
 // integrate_batch_full: fantasy_integrate_batch_ord2_full, cuda_geodesic.py:604-625.
-// One ray per thread; row `step` holds q1 *before* the test (the terminal state is stored, the
-// state after the last of `steps` steps is not).  out_traj must be pre-zeroed (np.zeros, :649).
+// Row `step` of a ray holds q1 *before* the termination test of that step (the terminal state is stored, the state
+// after the last of `steps` steps is not); rows after a ray's last stored row are left untouched (the host entry point
+// copies only the stored rows into the caller's np.zeros buffer, the _dev one zero-fills on request).
+//
+// The path is bound by the FP64 pipe like the render (the same B C B A(d) loop body: 1.6e11 steps/s at best) and writes
+// 32 B per step per ray, i.e. up to 5 TB/s of the 6.5 TB/s HBM write bandwidth when the GPU is full -- so the stores
+// must not cost issue slots or sector efficiency: one ray per thread, rows staged in shared memory four steps at a
+// time (2 STS.128 per step, XOR-swizzled: conflict-free) and flushed by the warp as FULL 128-BYTE LINES (8 lanes x 16 B
+// per ray and group, 8 coalesced STG.128 per thread every 4 steps, streaming).  Lanes whose ray has ended sit on the
+// fixed point of the flows (park) until the warp's last ray ends; the planar fast path is used when the rays allow it.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+template <bool kPlanar>
+__global__ void __launch_bounds__(kBlock, kPlanar ? SCHW_MINBLOCKS : SCHW_MINBLOCKS_GENERAL)
 integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__ p0s, long long n,
                       const __grid_constant__ StepParams P, double *__restrict__ out_traj,
-                      long long *__restrict__ out_rows, Counters *ctr)
+                      long long *__restrict__ out_rows, Counters *ctr, const int *__restrict__ select, int want)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (select && *select != want) return;                 // (grid-uniform) see batch_probe_kernel
+    constexpr int kWarps = kBlock / 32;
+    __shared__ double2 s_stage[kWarps][32 * 8];            // per warp: 32 rays x (4 rows x 32 B) = 4 KB, 16-byte pieces
+    __shared__ int s_rows[kBlock];                         // rows stored by the ray of each lane (INT_MAX while it runs)
+    __shared__ unsigned long long s_total;
+    __shared__ Memo2 s_memo[kPlanar ? kBlock : 1];
+    if (threadIdx.x == 0) s_total = 0ull;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * kBlock + threadIdx.x;
+    const long long ray0 = i - lane;                       // first ray of this warp
+    Memo2 M_reg;
+    Memo2 &M = kPlanar ? s_memo[threadIdx.x] : M_reg;
+    M.init(P.delta, P.h);
     RayState S;
-    {
-        const double q0[4] = {q0s[4 * i], q0s[4 * i + 1], q0s[4 * i + 2], q0s[4 * i + 3]};
-        const double p0[4] = {p0s[4 * i], p0s[4 * i + 1], p0s[4 * i + 2], p0s[4 * i + 3]};
+    bool active = i < n && P.steps > 0;
+    if (active) {
+        const double2 *q = reinterpret_cast<const double2 *>(q0s + 4 * i), *p = reinterpret_cast<const double2 *>(p0s + 4 * i);
+        const double2 qa = __ldg(q), qb = __ldg(q + 1), pa = __ldg(p), pb = __ldg(p + 1);
+        const double q0[4] = {qa.x, qa.y, qb.x, qb.y}, p0[4] = {pa.x, pa.y, pb.x, pb.y};
         init_state(S, q0, p0);
+    } else {
+        park(S, P);
     }
-    Memo2 M;      // unused (kMemo = false): the trajectory kernel is store-bound
-    double2 *row = reinterpret_cast<double2 *>(out_traj + (size_t)i * (size_t)P.steps * 4);
-    long long rows = 0;
-    bool fresh = true;
-    for (int step = 0; step < P.steps; ++step) {
-        __stcs(row + 2 * (size_t)step, make_double2(S.q1t, S.q1r));
-        __stcs(row + 2 * (size_t)step + 1, make_double2(S.q1h, S.q1p));
-        rows = step + 1;
-        if (terminated(S.q1r, P)) break;
-        if (!(S.q1r == S.q1r)) {
-            // NaN never terminates in the reference: every later row is NaN
-            const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-            for (int s2 = step + 1; s2 < P.steps; ++s2) {
-                __stcs(row + 2 * (size_t)s2, make_double2(nanv, nanv));
-                __stcs(row + 2 * (size_t)s2 + 1, make_double2(nanv, nanv));
+    s_rows[threadIdx.x] = active ? 0x7fffffff : 0;
+    int pp_hi = active ? P.pl_pp_hi : 0, tok = 0, n_general = 0, it = 0;
+    double2 *stage = s_stage[warp];
+    const int *rows_w = s_rows + (threadIdx.x & ~31);
+    bool first = true;
+    for (int step = 0;; ++step) {                          // (warp-uniform trip count)
+        const int slot = step & 3;
+        if (active) {                                      // row `step`: q1 before the test
+            stage[lane * 8 + ((2 * slot) ^ (lane & 7))] = make_double2(S.q1t, S.q1r);
+            stage[lane * 8 + ((2 * slot + 1) ^ (lane & 7))] = make_double2(S.q1h, S.q1p);
+            const bool nan_r = !(S.q1r == S.q1r);
+            if (terminated(S.q1r, P) || step == P.steps - 1) {
+                active = false; pp_hi = 0;
+                s_rows[threadIdx.x] = step + 1;
+                atomicAdd(&s_total, (unsigned long long)step);
+                park(S, P);
+            } else if (nan_r) {
+                // a NaN r never terminates in the reference: every later row is NaN
+                const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+                S.q1t = S.q1h = S.q1p = S.q2t = S.q2r = S.q2h = S.q2p = nanv;
             }
-            rows = P.steps;
-            break;
         }
-        flow_A<false>(S, fresh ? P.h : P.delta, fresh ? P.h_rs : P.d_rs, P.rs, M);
-        fresh = false;
-        step_BCB<false>(S, P, M);
+        const bool any_active = __any_sync(kFull, active);
+        if (slot == 3 || !any_active) {                    // flush rows [step - slot, step] of the warp's 32 rays
+            __syncwarp();
+            const int base = step - slot;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int L = 4 * j + (int)(lane >> 3), piece = (int)(lane & 7);
+                const int gstep = base + (piece >> 1);
+                if ((piece >> 1) <= slot && gstep < rows_w[L]) {
+                    const double2 v = stage[L * 8 + (piece ^ (L & 7))];
+                    __stcs(reinterpret_cast<double2 *>(out_traj + ((size_t)(ray0 + L) * (size_t)P.steps + (size_t)base) * 4) + piece, v);
+                }
+            }
+            __syncwarp();
+        }
+        if (!any_active) break;
+        // one step: A(d/2) B C B A(d/2) = [leading A(d/2) once] then B(d/2) C(d) B(d/2) A(d) with the merged A (A never
+        // touches q1, so q1 after B C B is the row of the next step whatever A follows)
+        if (first) { flow_A<false>(S, P.h, P.h_rs, P.rs, M); first = false; }
+        if (kPlanar) {
+            bool next = false;
+            step_BCBA_planar(S, P, M, pp_hi, tok, next, n_general);
+            tok = __all_sync(kFull, next);
+        } else {
+            step_BCB<true>(S, P, M);
+            flow_A<true>(S, P.delta, P.d_rs, P.rs, M);
+        }
+        ++it;
     }
-    if (out_rows) out_rows[i] = rows;
-    atomicAdd(&ctr->total_steps, (unsigned long long)(rows > 0 ? rows - 1 : 0));
+    if (i < n && out_rows) out_rows[i] = s_rows[threadIdx.x];
+    if (lane == 0 && it) {
+        atomicAdd(&ctr->warp_iters, (unsigned long long)it);
+        if (kPlanar) atomicAdd(&ctr->planar_iters, (unsigned long long)(it - n_general));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_total) atomicAdd(&ctr->total_steps, s_total);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -740,6 +798,46 @@ dfma_probe_kernel(double *out, int iters, double b, double c)
 #pragma unroll
     for (int u = 0; u < kChains; ++u) sum += a[u];
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step-loop probe (measurement only): the loop body of the render kernel on R rays per thread, without queue, refill or
+// epilogue -- how many SM cycles a warp-step costs as a function of rays per thread and resident CTAs (DESIGN.md §4.1:
+// is the step loop limited by the FP64 pipe, by issue slots or by dependent-issue latency?).
+// ---------------------------------------------------------------------------------------------
+template <int R, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
+step_probe_kernel(const __grid_constant__ StepParams P, int iters, double *__restrict__ out)
+{
+    __shared__ Memo2 s_memo[R * kBlock];
+    RayState S[R];
+    int pp_hi[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s_memo[r * kBlock + threadIdx.x].init(P.delta, P.h);
+        // camera-like rays of the default scene (utils.py:148-194) at angles 15..45 degrees, different per thread and slot
+        const double al = 0.26 + 0.52 * ((threadIdx.x * 7 + r * 131 + blockIdx.x * 13) % 1024) / 1024.0;
+        const double r0 = 30.0, f = 1.0 - P.rs / r0;
+        const double pr = -cos(al) * sqrt(f), pph = sin(al) * r0;
+        const double Cq = f * pr * pr + pph * pph / (r0 * r0);
+        const double q0[4] = {0.0, r0, 1.5707963267948966, 0.0}, p0[4] = {sqrt(4.0 * Cq / f) / (2.0 / f), pr, -0.0, pph};
+        init_state(S[r], q0, p0);
+        pp_hi[r] = P.pl_pp_hi;
+        flow_A<false>(S[r], P.h, P.h_rs, P.rs, s_memo[r * kBlock + threadIdx.x]);
+    }
+    int tok = 0, n_general = 0;
+    for (int it = 0; it < iters; ++it) {
+        bool next = false;
+        step_BCBA_planar_n<R>(S, P, &s_memo[threadIdx.x], kBlock, pp_hi, tok, next, n_general);
+        bool maybe = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) maybe |= maybe_finished(S[r].q1r, P);
+        tok = __all_sync(kFull, next & !maybe);
+    }
+    double acc = (double)n_general;
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc += S[r].q1t + S[r].q1r + S[r].q1p + S[r].p1t + S[r].p1r + S[r].p1h;
+    out[(size_t)blockIdx.x * kBlock + threadIdx.x] = acc;
 }
 
 }  // namespace schw
@@ -1254,6 +1352,52 @@ extern "C" int schw_integrate_batch(schw_handle *h, const double *q0s, const dou
 }
 
 // ---- integrate_batch_full -----------------------------------------------------------------------
+static int integrate_full_impl(schw_handle *h, const double *d_q0s, const double *d_p0s, int64_t n, const StepParams &P0,
+                               double *d_traj, long long *d_rows, cudaStream_t st)
+{
+    StepParams P = P0;
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
+    begin_timed(h, st);
+    if (P.pl_enable && trig_memo_enabled() && !planar_forced()) {
+        // the device chooses between the kernel with the planar fast path and the plain one (batch_probe_kernel)
+        batch_probe_kernel<<<1, 256, 0, st>>>(d_q0s, d_p0s, (long long)n, &h->ctr->batch_planar);
+        integrate_full_kernel<true><<<grid, kBlock, 0, st>>>(d_q0s, d_p0s, (long long)n, P, d_traj, d_rows, h->ctr, &h->ctr->batch_planar, 1);
+        P.pl_enable = 0;
+        integrate_full_kernel<false><<<grid, kBlock, 0, st>>>(d_q0s, d_p0s, (long long)n, P, d_traj, d_rows, h->ctr, &h->ctr->batch_planar, 0);
+        h->launches += 3;
+    } else if (P.pl_enable && trig_memo_enabled()) {
+        integrate_full_kernel<true><<<grid, kBlock, 0, st>>>(d_q0s, d_p0s, (long long)n, P, d_traj, d_rows, h->ctr, nullptr, 0);
+        h->launches += 1;
+    } else {
+        P.pl_enable = 0;
+        integrate_full_kernel<false><<<grid, kBlock, 0, st>>>(d_q0s, d_p0s, (long long)n, P, d_traj, d_rows, h->ctr, nullptr, 0);
+        h->launches += 1;
+    }
+    CU(cudaGetLastError());
+    end_timed(h, st);
+    return SCHW_OK;
+}
+
+extern "C" int schw_integrate_batch_full_dev(schw_handle *h, const double *d_q0s, const double *d_p0s, int64_t n,
+                                             int64_t steps, double delta, double rs, double r_max, double omega,
+                                             double *d_out_traj, int64_t *d_out_rows, int zero_fill, void *cuda_stream)
+{
+    if (!h) return fail(SCHW_E_INVALID, "null handle");
+    if (n < 0 || n > 0x7fffffffLL) return fail(SCHW_E_INVALID, "n must be in [0, 2^31-1]");
+    if (n > 0 && (!d_q0s || !d_p0s || (!d_out_traj && steps > 0))) return fail(SCHW_E_INVALID, "null array");
+    CU(cudaSetDevice(h->device));
+    StepParams P;
+    int rc = make_step_params(steps, delta, rs, r_max, omega, P);
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+    if (n == 0 || steps == 0) return SCHW_OK;
+    if (zero_fill) CU(cudaMemsetAsync(d_out_traj, 0, (size_t)n * (size_t)steps * 32, st));      // np.zeros, cuda_geodesic.py:649
+    long long *d_rows = (long long *)d_out_rows;
+    if (!d_rows) { ENSURE(h->rows, (size_t)n * sizeof(long long)); d_rows = (long long *)h->rows.p; }
+    return integrate_full_impl(h, d_q0s, d_p0s, n, P, d_out_traj, d_rows, st);
+}
+
 extern "C" int schw_integrate_batch_full(schw_handle *h, const double *q0s, const double *p0s, int64_t n,
                                          int64_t steps, double delta, double rs, double r_max, double omega,
                                          double *out_traj, int64_t *out_rows)
@@ -1272,15 +1416,10 @@ extern "C" int schw_integrate_batch_full(schw_handle *h, const double *q0s, cons
     cudaStream_t st = h->stream;
     CU(cudaMemcpyAsync(h->in_a.p, q0s, b, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(h->in_b.p, p0s, b, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
-    begin_timed(h, st);
     // No device-side zero fill: only the stored rows are copied back into the caller's np.zeros buffer.
-    integrate_full_kernel<<<(unsigned)((n + 31) / 32), 32, 0, st>>>((const double *)h->in_a.p, (const double *)h->in_b.p,
-                                                                      (long long)n, P, (double *)h->traj.p,
-                                                                      (long long *)h->rows.p, h->ctr);
-    h->launches += 1;
-    CU(cudaGetLastError());
-    end_timed(h, st);
+    rc = integrate_full_impl(h, (const double *)h->in_a.p, (const double *)h->in_b.p, n, P, (double *)h->traj.p,
+                             (long long *)h->rows.p, st);
+    if (rc) return rc;
     long long *rows = (long long *)malloc((size_t)n * sizeof(long long));
     if (!rows) return fail(SCHW_E_NOMEM, "host malloc");
     cudaError_t e = cudaMemcpyAsync(rows, h->rows.p, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, st);
@@ -2063,5 +2202,53 @@ extern "C" int schw_fp64_peak_probe(schw_handle *h, double *tflops, float *ms_ou
     h->timed = true; h->launches = 15;
     *tflops = best_tflops;
     if (ms_out) *ms_out = best;
+    return SCHW_OK;
+}
+
+// ---- step-loop probe (diagnostic) -----------------------------------------------------------------
+// variant: rays per thread * 100 + CTAs per SM requested (106, 105, 203, 204).  Returns kernel ms and the warp-steps run.
+extern "C" int schw_step_probe(schw_handle *h, int variant, int iters, double delta, float *ms, uint64_t *warp_steps,
+                               int *ctas_per_sm, int *regs)
+{
+    if (!h || !ms || !warp_steps) return fail(SCHW_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    StepParams P;
+    int rc = make_step_params(1 << 30, delta, 2.0, 1e6, 1.0, P);
+    if (rc) return rc;
+    ENSURE(h->in_c, (size_t)h->sm_count * 8 * kBlock * sizeof(double));
+    cudaStream_t st = h->stream;
+    const void *fn = nullptr;
+    switch (variant) {
+    case 106: fn = (const void *)step_probe_kernel<1, 6>; break;
+    case 105: fn = (const void *)step_probe_kernel<1, 5>; break;
+    case 104: fn = (const void *)step_probe_kernel<1, 4>; break;
+    case 203: fn = (const void *)step_probe_kernel<2, 3>; break;
+    case 204: fn = (const void *)step_probe_kernel<2, 4>; break;
+    case 202: fn = (const void *)step_probe_kernel<2, 2>; break;
+    default: return fail(SCHW_E_INVALID, "unknown probe variant");
+    }
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kBlock, 0));
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, fn));
+    const int want = variant % 100;
+    if (occ > want) occ = want;
+    const int blocks = h->sm_count * occ;
+    double *out = (double *)h->in_c.p;
+    void *args[] = {(void *)&P, (void *)&iters, (void *)&out};
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CU(cudaEventRecord(h->ev0, st));
+        CU(cudaLaunchKernel(fn, dim3(blocks), dim3(kBlock), args, 0, st));
+        CU(cudaEventRecord(h->ev1, st));
+        CU(cudaEventSynchronize(h->ev1));
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, h->ev0, h->ev1));
+        if (t < best) best = t;
+    }
+    *ms = best;
+    *warp_steps = (uint64_t)blocks * (kBlock / 32) * (uint64_t)iters;
+    if (ctas_per_sm) *ctas_per_sm = occ;
+    if (regs) *regs = fa.numRegs;
     return SCHW_OK;
 }

@@ -28,6 +28,7 @@ EXPORTS = (
     "schw_render_dedup", "schw_render_dedup_dev", "schw_last_dedup_stats",
     "schw_render_dev_pitched", "schw_last_status", "schw_flat_raytrace",
     "schw_dedup_plan_dev", "schw_dedup_integrate_dev", "schw_dedup_epilogue_dev", "schw_observer_q0",
+    "schw_integrate_batch_full_dev", "schw_step_probe",
 )
 
 
@@ -90,6 +91,7 @@ def load():
     L.schw_integrate_batch.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp]
     L.schw_integrate_batch_dev.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp, vp]
     L.schw_integrate_batch_full.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp]
+    L.schw_integrate_batch_full_dev.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, dp, vp, i32, vp]
     L.schw_integrate_batch_rows.argtypes = [vp, dp, dp, i64, i64, dbl, dbl, dbl, dbl, vp, i64, dp, vp]
     L.schw_initial_conditions.argtypes = [vp, scp, i32, i32, i32, dp, dp]
     L.schw_initial_conditions_px.argtypes = [vp, dp, dp, i64, dbl, dp, dp]
@@ -100,6 +102,7 @@ def load():
     L.schw_last_status.argtypes = [vp]
     L.schw_flat_raytrace.argtypes = [vp, dp, dp, i64, dbl, dbl, dbl, dbl, dbl, i32, i32, vp, i32, i32, vp, vp, i64, i64, dp]
     L.schw_observer_q0.argtypes = [scp, dp]
+    L.schw_step_probe.argtypes = [vp, i32, i32, dbl, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.schw_dedup_plan_dev.argtypes = [vp, scp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp]
     L.schw_dedup_integrate_dev.argtypes = [vp, scp, i32, vp, vp, vp]
     L.schw_dedup_epilogue_dev.argtypes = [vp, scp, vp, i32, i32, i32, vp, i64, vp, i64, xop, vp, vp, vp]
@@ -257,6 +260,12 @@ class Handle:
         _check(self._L.schw_fp64_peak_probe(self._h, C.byref(t), C.byref(ms)))
         return t.value, ms.value
 
+    def step_probe(self, variant, iters=20000, delta=0.01):
+        """The render kernel's loop body alone: dict(ms, warp_steps, ctas_per_sm, regs, rays_per_thread)."""
+        ms, ws, occ, regs = C.c_float(), C.c_uint64(), C.c_int(), C.c_int()
+        _check(self._L.schw_step_probe(self._h, int(variant), int(iters), float(delta), C.byref(ms), C.byref(ws), C.byref(occ), C.byref(regs)))
+        return dict(ms=ms.value, warp_steps=int(ws.value), ctas_per_sm=occ.value, regs=regs.value, rays_per_thread=variant // 100)
+
     def math_probe(self, x):
         x = np.ascontiguousarray(x, np.float64)
         r, s, c = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
@@ -291,6 +300,12 @@ class Handle:
         _check(self._L.schw_integrate_batch_full(self._h, _p(q0s), _p(p0s), n, int(steps), float(delta), float(rs),
                                                  float(r_max), float(omega), _p(traj), _p(rows)))
         return (traj, rows) if want_rows else traj
+
+    def integrate_batch_full_dev(self, d_q0s, d_p0s, n, steps, delta, rs, r_max, omega, d_traj, d_rows=0, zero_fill=False, stream=0):
+        """Device-pointer integrate_batch_full: (n, steps, 4) f64 in HBM; enqueue only."""
+        _check(self._L.schw_integrate_batch_full_dev(self._h, C.c_void_p(d_q0s), C.c_void_p(d_p0s), int(n), int(steps),
+                                                     float(delta), float(rs), float(r_max), float(omega), C.c_void_p(d_traj),
+                                                     C.c_void_p(d_rows or None), int(bool(zero_fill)), C.c_void_p(stream or None)))
 
     def integrate_batch_rows(self, q0s, p0s, steps, delta, rs, r_max, omega, row_idx, want_rows=False):
         """Rows `row_idx` (strictly ascending step indices) of integrate_batch_full's result, (n, len(row_idx), 4)."""

@@ -83,7 +83,7 @@ def test_integrate_batch_edge_cases(handle, orc):
         handle.integrate_batch(np.zeros((3, 3)), np.zeros((3, 3)), 1, 0.1, 2.0, 3.0, 1.0)
 
 
-def test_single_ray_trajectory_k3(handle, golden):
+def test_single_ray_trajectory_k3(handle, orc, golden):
     """BASELINE config 2: single_ray_cuda_test.py parameters, per-step state match."""
     k = golden("single_ray_k3.npz")
     traj, rows = handle.integrate_batch_full(k["q0"][None], k["p0"][None], int(k["steps"]), float(k["delta"]), 2.0,
@@ -104,7 +104,7 @@ def test_single_ray_trajectory_k3(handle, golden):
     assert not traj[0, rows[0]:].any()                 # zero rows after termination
 
 
-def test_trajectories_vs_einsteinpy_kats(handle, golden):
+def test_trajectories_vs_einsteinpy_kats(handle, orc, golden):
     from test_oracle_golden import _null_pt
     k = golden("kat_k1_einsteinpy_trajectory.npz")
     q0 = k["q0"]; p0 = np.array([_null_pt(q0, k["p_sph"]), *k["p_sph"]])

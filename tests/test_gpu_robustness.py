@@ -86,3 +86,40 @@ def test_texture_flag_that_never_arrives_is_an_error_not_a_wrong_frame(handle):
                       d_tex_ready=flag.data_ptr())
     handle.last_status()
     assert (d_cls.cpu().numpy() == handle.render(sc, np.zeros((h, w, 3), np.uint8))["cls"]).all()
+
+
+def test_integrate_batch_full_dev_equals_the_host_entry_point(handle):
+    """schw_integrate_batch_full_dev (trajectories staged in shared memory, flushed as full 128-byte lines) on a ragged
+    batch: ray count not a multiple of the CTA, step count not a multiple of the 4-row group, rays ending at every
+    position of a group, a NaN ray, rays that end before the first step -- against the host entry point (np.zeros rows
+    after termination) and against integrate_batch (the state after k steps = row k)."""
+    import torch
+    from helpers import random_rays
+    q0s, p0s = random_rays(301, seed=17)
+    q0s[7, 1] = np.nan                       # never terminates in the reference: NaN rows up to the step cap
+    q0s[11, 1] = 2.0                         # starts inside the capture radius: one row
+    steps, delta, rs, r_max, omega = 1003, 0.05, 2.0, 41.0, 1.0
+    want, rows_want = handle.integrate_batch_full(q0s, p0s, steps, delta, rs, r_max, omega, want_rows=True)
+    dq, dp = torch.from_numpy(q0s).cuda(), torch.from_numpy(p0s).cuda()
+    traj = torch.full((301, steps, 4), 7.0, dtype=torch.float64, device="cuda")
+    rows = torch.zeros(301, dtype=torch.int64, device="cuda")
+    st = torch.cuda.Stream()
+    handle.integrate_batch_full_dev(dq.data_ptr(), dp.data_ptr(), 301, steps, delta, rs, r_max, omega, traj.data_ptr(),
+                                    rows.data_ptr(), zero_fill=True, stream=st.cuda_stream)
+    handle.last_status()
+    assert np.array_equal(rows.cpu().numpy(), rows_want)
+    assert np.array_equal(traj.cpu().numpy(), want, equal_nan=True)
+    assert rows_want[11] == 1 and rows_want[7] == steps and np.isnan(want[7, 5:]).all()
+    assert len(set(int(r) % 4 for r in rows_want)) == 4           # every flush position of a 4-row group occurs
+    # without the zero fill the rows past a ray's end are left as they were
+    traj.fill_(7.0)
+    handle.integrate_batch_full_dev(dq.data_ptr(), dp.data_ptr(), 301, steps, delta, rs, r_max, omega, traj.data_ptr(),
+                                    rows.data_ptr(), stream=st.cuda_stream)
+    handle.last_status()
+    got = traj.cpu().numpy()
+    for i in (0, 11, 100, 300):
+        assert np.array_equal(got[i, :rows_want[i]], want[i, :rows_want[i]], equal_nan=True) and (got[i, rows_want[i]:] == 7.0).all()
+    k = 57
+    fin = handle.integrate_batch(q0s, p0s, k, delta, rs, r_max, omega)
+    live = rows_want > k
+    assert np.array_equal(fin[live], want[live, k], equal_nan=True)

@@ -41,8 +41,7 @@ def main():
     ksrc = open(os.path.join(PKG, "csrc", "schw_kernels.cu")).read().splitlines()
     dsrc = open(os.path.join(PKG, "csrc", "schw_device.cuh")).read().splitlines()
     call_lines = [i + 1 for i, l in enumerate(ksrc) if "step_BCBA_planar(" in l and "//" not in l.split("step_BCBA_planar(")[0]]
-    assert len(call_lines) == 1, call_lines
-    call_line = call_lines[0]
+    assert call_lines, "no call of step_BCBA_planar in schw_kernels.cu"      # (one per kernel that uses it; KERNEL selects)
     with tempfile.TemporaryDirectory() as d:
         subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(a.lib)], cwd=d, stdout=subprocess.DEVNULL)
         cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
@@ -71,10 +70,11 @@ def main():
             continue
         fresh = True
         bra_div += m.group(3).startswith("BRA.DIV")
-        if ("schw_kernels.cu", call_line) not in chain:
+        hits = [c for c in chain if c[0] == "schw_kernels.cu" and c[1] in call_lines]
+        if not hits:
             continue
         # the call site inside step_BCBA_planar = the chain entry right below the kernel's call
-        k = chain.index(("schw_kernels.cu", call_line))
+        k = chain.index(hits[0])
         site = chain[k - 1] if k > 0 else None
         text = dsrc[site[1] - 1] if site and site[0] == "schw_device.cuh" else ""
         deeper = " ".join(dsrc[c[1] - 1] for c in chain[:k] if c[0] == "schw_device.cuh")
