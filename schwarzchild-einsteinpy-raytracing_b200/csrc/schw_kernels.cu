@@ -74,6 +74,7 @@ struct BatchJob {
     __device__ __forceinline__ bool skip() const { return select && *select != want; }
     __device__ __forceinline__ const unsigned *ready_flag() const { return nullptr; }
     __device__ __forceinline__ unsigned *err_word() const { return nullptr; }
+    __device__ __forceinline__ bool whole_tiles() const { return false; }
     __device__ __forceinline__ bool ends_at_once(const StepParams &) const { return false; }
     __device__ __forceinline__ long long queue_len() const { return n; }
     __device__ __forceinline__ long long resolve(long long q) const { return q; }
@@ -135,12 +136,18 @@ struct RenderJob {
     // pixel (q & 31) of tile tile_order[q >> 5]; slots past the end of a row are empty.
     const int32_t *__restrict__ tile_order;
     int32_t tiles_per_row;
+    // Refill policy.  0: every lane takes its next ray the moment its own ray ends (best when a lane handles many rays: the
+    // lanes of a warp drift apart, but the queue keeps them all busy).  1: a warp takes a whole 32-pixel tile only when all
+    // its rays have ended -- neighbouring pixels need almost the same number of steps, so the warp stays full until it
+    // retires and the frame does not end with every warp carrying a few stragglers (small frames / shards: few rays per lane).
+    int32_t tile_mode;
     long long qlen;
 
     __device__ __forceinline__ bool skip() const { return false; }
     // the flag a warp must see before its first epilogue (texel lookup), or NULL
     __device__ __forceinline__ const unsigned *ready_flag() const { return tex_ready; }
     __device__ __forceinline__ unsigned *err_word() const { return err; }
+    __device__ __forceinline__ bool whole_tiles() const { return tile_mode != 0; }
     // every ray of the frame starts at r_obs: do the rays end before their first step (cuda_geodesic.py:598)?
     __device__ __forceinline__ bool ends_at_once(const StepParams &P) const { return P.steps <= 0 || terminated(sc.r_obs, P); }
     __device__ __forceinline__ long long queue_len() const { return qlen; }
@@ -262,8 +269,12 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
             job.store(k, a.x, a.y, b.x, b.y, s_nsteps[threadIdx.x], !(a.y == a.y), slot);
             waiting = false; k = -1;
         }
+        // (whole tiles only: nobody is refilled while a ray of the warp is still running, see RenderJob::tile_mode; voted
+        //  once, outside the refill loop -- a second vote inside it costs the compiler its proof that the step loop's votes
+        //  are reached convergently, and with it 13 % of the frame time: tests/test_abi_symbols.py::test_step_loop_sass_budget)
+        const bool hold = job.whole_tiles() && __any_sync(kFull, active);
         while (true) {                                             // loop: a ray may end at step 0
-            const unsigned need = __ballot_sync(kFull, !active && !drained);
+            const unsigned need = __ballot_sync(kFull, !active && !drained && !hold);
             if (need == 0u) break;
             long long base = 0;
             const int leader = __ffs(need) - 1;
@@ -335,7 +346,7 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
                 // Service now if nobody is left integrating, or once the accumulated idle cost reaches the cost of
                 // one (divergent) service pass -- the ski-rental rule: waiting never costs more than 2x the optimum.
                 if ((wm != 0u || any_done) &&
-                    (debt >= Job::kServiceCost || __ballot_sync(kFull, active) == 0u)) break;
+                    ((debt >= Job::kServiceCost && !job.whole_tiles()) || __ballot_sync(kFull, active) == 0u)) break;
             }
         }
     }
@@ -396,35 +407,48 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
     int pp_hi = active ? P.pl_pp_hi : 0, tok = 0, n_general = 0, it = 0;
     double2 *stage = s_stage[warp];
     const int *rows_w = s_rows + (threadIdx.x & ~31);
+    // flush geometry of this lane: in store j (0..7) it writes 16-byte piece `piece` of the 128-byte group of the warp's ray
+    // L = 4 j + l3, read from the swizzled staging slot L*8 + (piece ^ (L & 7)), (L & 7) = 4 (j & 1) + l3
+    const int l3 = (int)(lane >> 3), piece = (int)(lane & 7);
+    double2 *const dst0 = reinterpret_cast<double2 *>(out_traj + (size_t)(ray0 + l3) * (size_t)P.steps * 4) + piece;
+    const size_t dstride = (size_t)4 * (size_t)P.steps * 2;       // double2 units between the rays of store j and store j+1
+    const int sidx0 = l3 * 8 + (piece ^ l3), sidx1 = (4 + l3) * 8 + (piece ^ (4 + l3));
     bool first = true;
     for (int step = 0;; ++step) {                          // (warp-uniform trip count)
         const int slot = step & 3;
         if (active) {                                      // row `step`: q1 before the test
             stage[lane * 8 + ((2 * slot) ^ (lane & 7))] = make_double2(S.q1t, S.q1r);
             stage[lane * 8 + ((2 * slot + 1) ^ (lane & 7))] = make_double2(S.q1h, S.q1p);
-            const bool nan_r = !(S.q1r == S.q1r);
-            if (terminated(S.q1r, P) || step == P.steps - 1) {
-                active = false; pp_hi = 0;
-                s_rows[threadIdx.x] = step + 1;
-                atomicAdd(&s_total, (unsigned long long)step);
-                park(S, P);
-            } else if (nan_r) {
-                // a NaN r never terminates in the reference: every later row is NaN
-                const double nanv = __longlong_as_double(0x7ff8000000000000LL);
-                S.q1t = S.q1h = S.q1p = S.q2t = S.q2r = S.q2h = S.q2p = nanv;
+            // integer pre-test on the high word of r (maybe_finished), the exact FP64 test only when it cannot rule the end out
+            if (maybe_finished(S.q1r, P) || step == P.steps - 1) {
+                if (terminated(S.q1r, P) || step == P.steps - 1) {
+                    active = false; pp_hi = 0;
+                    s_rows[threadIdx.x] = step + 1;
+                    atomicAdd(&s_total, (unsigned long long)step);
+                    park(S, P);
+                } else if (!(S.q1r == S.q1r)) {
+                    // a NaN r never terminates in the reference: every later row is NaN
+                    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+                    S.q1t = S.q1h = S.q1p = S.q2t = S.q2r = S.q2h = S.q2p = nanv;
+                }
             }
         }
         const bool any_active = __any_sync(kFull, active);
         if (slot == 3 || !any_active) {                    // flush rows [step - slot, step] of the warp's 32 rays
             __syncwarp();
             const int base = step - slot;
+            // all four rows of all 32 rays are valid (the usual case): eight unconditional full-line stores
+            if (__all_sync(kFull, slot == 3 && s_rows[threadIdx.x] > step)) {
+                double2 *dst = dst0 + (size_t)base * 2;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int L = 4 * j + (int)(lane >> 3), piece = (int)(lane & 7);
-                const int gstep = base + (piece >> 1);
-                if ((piece >> 1) <= slot && gstep < rows_w[L]) {
-                    const double2 v = stage[L * 8 + (piece ^ (L & 7))];
-                    __stcs(reinterpret_cast<double2 *>(out_traj + ((size_t)(ray0 + L) * (size_t)P.steps + (size_t)base) * 4) + piece, v);
+                for (int j = 0; j < 8; ++j) __stcs(dst + j * dstride, stage[32 * j + ((j & 1) ? sidx1 - 32 : sidx0)]);
+            } else {
+#pragma unroll 1
+                for (int j = 0; j < 8; ++j) {
+                    const int L = 4 * j + l3;
+                    const int gstep = base + (piece >> 1);
+                    if ((piece >> 1) <= slot && gstep < rows_w[L])
+                        __stcs(dst0 + (size_t)base * 2 + j * dstride, stage[L * 8 + (piece ^ (L & 7))]);
                 }
             }
             __syncwarp();
@@ -1631,6 +1655,17 @@ static int build_tile_order(schw_handle *h, const schw_scene *s, const ScenePara
 
 // SCHW_LPT_ORDER=0: plain row-major queue (A/B measurements)
 static bool lpt_order_enabled() { return env_switch_on("SCHW_LPT_ORDER"); }
+// Refill policy of the render queue (RenderJob::tile_mode).  SCHW_TILE_MODE=0/1 forces it (A/B measurements); by default
+// whole tiles are used when a lane gets fewer than SCHW_TILE_BELOW rays on average.
+static int tile_mode_for(const schw_handle *h, long long n)
+{
+    const char *e = getenv("SCHW_TILE_MODE");
+    if (e && (e[0] == '0' || e[0] == '1')) return e[0] - '0';
+    const char *b = getenv("SCHW_TILE_BELOW");
+    const double below = b ? atof(b) : 0.0;
+    const double rays_per_lane = (double)n / ((double)h->sm_count * 6 * kBlock);
+    return rays_per_lane < below ? 1 : 0;
+}
 
 // ---- fused render -------------------------------------------------------------------------------
 extern "C" int schw_render_dev_pitched(schw_handle *h, const schw_scene *scene, const uint8_t *d_tex, int row_begin,
@@ -1668,12 +1703,13 @@ extern "C" int schw_render_dev_pitched(schw_handle *h, const schw_scene *scene, 
     job.texel = x ? x->texel : nullptr;
     job.nsteps = x ? x->nsteps : nullptr;
     job.n = n;
-    job.tile_order = nullptr; job.tiles_per_row = 1; job.qlen = n;
+    job.tile_order = nullptr; job.tiles_per_row = 1; job.qlen = n; job.tile_mode = 0;
     if (n > 0 && lpt_order_enabled()) {
         const int32_t *d_order = nullptr;
         rc = build_tile_order(h, scene, sc, st, &d_order, &job.tiles_per_row, &job.qlen);
         if (rc) return rc;
         job.tile_order = d_order;
+        job.tile_mode = tile_mode_for(h, n);
     }
     begin_timed(h, st);
     rc = launch_persistent(h, job, P, h->occ_render, st);
@@ -1862,7 +1898,7 @@ static int dedup_epilogue(schw_handle *h, const schw_scene *scene, const uint8_t
     job.texel = x ? x->texel : nullptr;
     job.nsteps = x ? x->nsteps : nullptr;
     job.n = n;
-    job.tile_order = nullptr; job.tiles_per_row = 1; job.qlen = n;
+    job.tile_order = nullptr; job.tiles_per_row = 1; job.qlen = n; job.tile_mode = 0;
     CU(cudaMemsetAsync(&h->ctr->pixel_steps, 0, sizeof(unsigned long long), st));
     dedup_epilogue_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, st>>>(job, (const int *)h->dd_map.p, prb, prs,
                                                                                   d_fq_all, d_ns_all, h->ctr);
@@ -2222,6 +2258,10 @@ extern "C" int schw_step_probe(schw_handle *h, int variant, int iters, double de
     case 106: fn = (const void *)step_probe_kernel<1, 6>; break;
     case 105: fn = (const void *)step_probe_kernel<1, 5>; break;
     case 104: fn = (const void *)step_probe_kernel<1, 4>; break;
+    case 103: fn = (const void *)step_probe_kernel<1, 3>; break;
+    case 102: fn = (const void *)step_probe_kernel<1, 2>; break;
+    case 101: fn = (const void *)step_probe_kernel<1, 1>; break;
+    case 201: fn = (const void *)step_probe_kernel<2, 1>; break;
     case 203: fn = (const void *)step_probe_kernel<2, 3>; break;
     case 204: fn = (const void *)step_probe_kernel<2, 4>; break;
     case 202: fn = (const void *)step_probe_kernel<2, 2>; break;

@@ -13,14 +13,16 @@ sys.path.insert(0, os.path.join(ROOT, "schwarzchild-einsteinpy-raytracing_b200")
 import schw_b200  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--iters", type=int, default=4000)
+ap.add_argument("--iters", type=int, default=30000)
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 hd = schw_b200.Handle(0)
 info = hd.device_info()
 f = info["clock_khz"] * 1e3
 res = []
-for v in (106, 105, 104, 204, 203, 202):
+hd.fp64_peak_probe()            # warm-up: the SM clock has to be up before millisecond-long kernels are timed
+hd.step_probe(106, a.iters)
+for v in (106, 105, 104, 103, 102, 101, 204, 203, 202, 201, 106):
     r = hd.step_probe(v, a.iters)
     # an SM sub-partition hosts a quarter of the SM's warps: cycles it spends per warp-step of ONE ray
     warps_per_smsp = r["ctas_per_sm"] * 4 / 4.0
