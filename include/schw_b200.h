@@ -260,7 +260,7 @@ int  schw_math_probe(schw_handle *h, const double *x, int64_t n, double *rcp, do
  * variant = 100 * rays per thread + resident CTAs per SM requested (106, 105, 104, 204, 203, 202): kernel time and
  * warp-steps executed, from which SM cycles per warp-step follow. */
 int  schw_step_probe(schw_handle *h, int variant, int iters, double delta, float *ms, uint64_t *warp_steps,
-                     int *ctas_per_sm, int *regs);
+                     int *ctas_per_sm, int *regs, double *planar_fraction);
 
 /* Diagnostic, needs no device: the step parameters exactly as the kernels receive them (csrc/schw_device.cuh:
  * StepParams, incl. the thresholds of the planar fast path), for the host-compiled model of the step loop in

@@ -38,6 +38,8 @@ struct alignas(16) StepParams {
     double pl_zero_hs;       // (+0) * mhs: the signed zero the mixed flow adds to p_theta when q1_theta == q2_theta
     double rcap;             // 1.1*rs evaluated in FP64           (cuda_geodesic.py:598)
     double r_max;
+    double park_r;           // radius at which lanes without a ray sit on the fixed point of the flows (make_step_params)
+    double _pad8;
     int32_t pl_ph_hi;        // |p_theta| <  T      <=  hi(|p_theta|) <  pl_ph_hi
     int32_t pl_r_hi;         // r         >= r_thr  <=  hi(r)         >= pl_r_hi   (signed compare)
     int32_t pl_pp_hi;        // |p_phi|   >  2^28 T <=  hi(|p_phi|)   >= pl_pp_hi

@@ -215,7 +215,7 @@ struct RenderJob {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void park(RayState &S, const StepParams &P)
 {
-    const double q0[4] = {0.0, 4.0 * P.rs + 8.0, 1.5707963267948966, 0.0}, p0[4] = {0.0, 0.0, 0.0, 0.0};
+    const double q0[4] = {0.0, P.park_r, 1.5707963267948966, 0.0}, p0[4] = {0.0, 0.0, 0.0, 0.0};
     init_state(S, q0, p0);
 }
 
@@ -242,7 +242,8 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
     Memo2 &M = kSmemMemo ? s_memo[threadIdx.x] : M_reg;
     M.init(P.delta, P.h);        // m1 serves the merged A(delta) of the step loop, m2 the two B(delta/2)
     int k = -1;                  // ray in flight, or finished ray awaiting service (n < 2^31 is checked on the host)
-    int n = 0;                   // steps taken by the ray in flight
+    int it_end = 0x7fffffff;     // value of `it` at which the ray in flight reaches the step cap (never, while parked); the
+                                 // steps it has taken are it - s_nsteps[threadIdx.x] (= `it` when it was fetched)
     bool active = false;         // integrating a ray
     bool waiting = false;        // ray finished: result parked in shared memory, epilogue + refill pending
     bool drained = false;        // queue is empty
@@ -300,7 +301,9 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
                             // leading A(d/2) of the ray's first step (cuda_geodesic.py:571); every later A is the merged
                             // trailing+leading A(d) at the end of the loop body.  Divergent code: no memo vote here.
                             flow_A<false>(S, P.h, P.h_rs, P.rs, M);
-                            k = kk; n = 0; active = true;
+                            k = kk; active = true;
+                            s_nsteps[threadIdx.x] = it;
+                            it_end = P.steps <= 0x7fffffff - it ? it + P.steps : 0x7fffffff;
                         }
                     }
                 } else {
@@ -322,15 +325,17 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
                 step_BCB<kMemo>(S, P, M);                           // q1 is now final for this step
                 flow_A<kMemo>(S, P.delta, P.d_rs, P.rs, M);         // trailing A(d/2) + next step's leading A(d/2)
             }
-            ++n; ++it;
+            ++it;
             // termination (cuda_geodesic.py:598): a two-compare integer pre-test on the high word of r every step, the exact
             // FP64 test only in the (rare) steps where some lane's pre-test cannot rule termination out
-            const bool maybe = active & ((n >= P.steps) | maybe_finished(S.q1r, P));
+            // (no `active &`: a parked lane has it_end = INT_MAX and sits at P.park_r, which passes the pre-test whenever a radius
+            //  strictly between the thresholds exists -- make_step_params; otherwise it only sends the warp to the exact test)
+            const bool maybe = (it >= it_end) | maybe_finished(S.q1r, P);
             const bool tick = (it & 15) == 0;
             // one vote per step on the fast path: "nobody may have finished and everybody may start the next step planar"
             if (kPlanar) tok = __all_sync(kFull, next & !maybe);
             if ((kPlanar && tok) ? tick : (__any_sync(kFull, maybe) || tick)) {
-                const bool done = maybe && (n >= P.steps || finished_or_nan(S.q1r, P));
+                const bool done = active && maybe && (it >= it_end || finished_or_nan(S.q1r, P));
                 const bool any_done = __any_sync(kFull, done);
                 // idle cost so far: every waiting lane wastes one lane-step per iteration (booked every 16 iterations)
                 const unsigned wm = __ballot_sync(kFull, waiting);
@@ -338,8 +343,10 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
                 if (done) {
                     s_fin[threadIdx.x] = make_double2(S.q1t, S.q1r);
                     s_fin[kBlock + threadIdx.x] = make_double2(S.q1h, S.q1p);
+                    const int n = it - s_nsteps[threadIdx.x];
                     s_nsteps[threadIdx.x] = n;
                     atomicAdd(&s_total, (unsigned long long)n);
+                    it_end = 0x7fffffff;
                     active = false; waiting = true; pp_hi = 0;
                     park(S, P);
                 }
@@ -831,37 +838,47 @@ dfma_probe_kernel(double *out, int iters, double b, double c)
 // ---------------------------------------------------------------------------------------------
 template <int R, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
-step_probe_kernel(const __grid_constant__ StepParams P, int iters, double *__restrict__ out)
+step_probe_kernel(const __grid_constant__ StepParams P, int rounds, int period, double *__restrict__ out, Counters *ctr)
 {
     __shared__ Memo2 s_memo[R * kBlock];
     RayState S[R];
     int pp_hi[R];
+    int n_general = 0, it = 0;
+    double acc = 0.0;
+    for (int round = 0; round < rounds; ++round) {
+        // camera-like rays of the default scene (utils.py:148-194) at angles 15..45 degrees, different per thread and slot;
+        // re-started every `period` steps so that they stay on the planar fast path like the rays of a frame (which end
+        // after 3-7 k steps), instead of winding on until p_theta outgrows its bound
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        s_memo[r * kBlock + threadIdx.x].init(P.delta, P.h);
-        // camera-like rays of the default scene (utils.py:148-194) at angles 15..45 degrees, different per thread and slot
-        const double al = 0.26 + 0.52 * ((threadIdx.x * 7 + r * 131 + blockIdx.x * 13) % 1024) / 1024.0;
-        const double r0 = 30.0, f = 1.0 - P.rs / r0;
-        const double pr = -cos(al) * sqrt(f), pph = sin(al) * r0;
-        const double Cq = f * pr * pr + pph * pph / (r0 * r0);
-        const double q0[4] = {0.0, r0, 1.5707963267948966, 0.0}, p0[4] = {sqrt(4.0 * Cq / f) / (2.0 / f), pr, -0.0, pph};
-        init_state(S[r], q0, p0);
-        pp_hi[r] = P.pl_pp_hi;
-        flow_A<false>(S[r], P.h, P.h_rs, P.rs, s_memo[r * kBlock + threadIdx.x]);
+        for (int r = 0; r < R; ++r) {
+            s_memo[r * kBlock + threadIdx.x].init(P.delta, P.h);
+            const double al = 0.26 + 0.52 * ((threadIdx.x * 7 + r * 131 + blockIdx.x * 13 + round * 17) % 1024) / 1024.0;
+            const double r0 = 30.0, f = 1.0 - P.rs / r0;
+            const double pr = -cos(al) * sqrt(f), pph = sin(al) * r0;
+            const double Cq = f * pr * pr + pph * pph / (r0 * r0);
+            const double q0[4] = {0.0, r0, 1.5707963267948966, 0.0}, p0[4] = {sqrt(4.0 * Cq / f) / (2.0 / f), pr, -0.0, pph};
+            init_state(S[r], q0, p0);
+            pp_hi[r] = P.pl_pp_hi;
+            flow_A<false>(S[r], P.h, P.h_rs, P.rs, s_memo[r * kBlock + threadIdx.x]);
+        }
+        int tok = 0;
+        for (int k = 0; k < period; ++k) {
+            bool next = false;
+            step_BCBA_planar_n<R>(S, P, &s_memo[threadIdx.x], kBlock, pp_hi, tok, next, n_general);
+            bool maybe = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) maybe |= maybe_finished(S[r].q1r, P);
+            tok = __all_sync(kFull, next & !maybe);
+            ++it;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc += S[r].q1t + S[r].q1r + S[r].q1p + S[r].p1t + S[r].p1r + S[r].p1h;
     }
-    int tok = 0, n_general = 0;
-    for (int it = 0; it < iters; ++it) {
-        bool next = false;
-        step_BCBA_planar_n<R>(S, P, &s_memo[threadIdx.x], kBlock, pp_hi, tok, next, n_general);
-        bool maybe = false;
-#pragma unroll
-        for (int r = 0; r < R; ++r) maybe |= maybe_finished(S[r].q1r, P);
-        tok = __all_sync(kFull, next & !maybe);
-    }
-    double acc = (double)n_general;
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc += S[r].q1t + S[r].q1r + S[r].q1p + S[r].p1t + S[r].p1r + S[r].p1h;
     out[(size_t)blockIdx.x * kBlock + threadIdx.x] = acc;
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&ctr->warp_iters, (unsigned long long)it);
+        atomicAdd(&ctr->planar_iters, (unsigned long long)(it - n_general));
+    }
 }
 
 }  // namespace schw
@@ -1177,6 +1194,15 @@ static int make_step_params(int64_t steps, double delta, double rs, double r_max
     // order like the doubles; otherwise (negative or NaN thresholds) the pre-test never rules termination out
     P.hi_rcap = (P.rcap >= 0.0) ? hi_word(P.rcap) : 0x7fffffff;
     P.hi_rmax = (P.r_max > 0.0) ? hi_word(P.r_max) : (int32_t)0x80000000;
+    // where lanes without a ray sit: a radius whose high word lies strictly between the two thresholds, so that the
+    // termination pre-test is false for them; if there is none (r_max within a few ulps of the capture radius, or
+    // degenerate thresholds) any finite radius does -- the pre-test then always sends the warp to the exact test, which
+    // looks at active lanes only
+    P.park_r = 4.0 * rs + 8.0;
+    if (P.hi_rcap >= 0 && P.hi_rmax > 0 && (int64_t)P.hi_rmax - (int64_t)P.hi_rcap >= 2 && P.hi_rmax < 0x7ff00000) {
+        const double mid = from_hi_word((int32_t)(((int64_t)P.hi_rcap + (int64_t)P.hi_rmax) / 2));
+        if (!(hi_word(P.park_r) > P.hi_rcap && hi_word(P.park_r) < P.hi_rmax)) P.park_r = mid;
+    }
     make_planar_params(P);
     return SCHW_OK;
 }
@@ -1655,16 +1681,13 @@ static int build_tile_order(schw_handle *h, const schw_scene *s, const ScenePara
 
 // SCHW_LPT_ORDER=0: plain row-major queue (A/B measurements)
 static bool lpt_order_enabled() { return env_switch_on("SCHW_LPT_ORDER"); }
-// Refill policy of the render queue (RenderJob::tile_mode).  SCHW_TILE_MODE=0/1 forces it (A/B measurements); by default
-// whole tiles are used when a lane gets fewer than SCHW_TILE_BELOW rays on average.
-static int tile_mode_for(const schw_handle *h, long long n)
+// Refill policy of the render queue (RenderJob::tile_mode): whole tiles by default -- measured faster at every frame size
+// (profiles/r02_ab_tile.json: 400x400 7.12 -> 6.81 ms, a 1/8 shard of the 4K frame 39.26 -> 39.02 ms, the 4K frame
+// 308.7 -> 306.1 ms, same output bits); SCHW_TILE_MODE=0 selects the per-lane refill (A/B measurements).
+static int tile_mode_for(const schw_handle *, long long)
 {
     const char *e = getenv("SCHW_TILE_MODE");
-    if (e && (e[0] == '0' || e[0] == '1')) return e[0] - '0';
-    const char *b = getenv("SCHW_TILE_BELOW");
-    const double below = b ? atof(b) : 0.0;
-    const double rays_per_lane = (double)n / ((double)h->sm_count * 6 * kBlock);
-    return rays_per_lane < below ? 1 : 0;
+    return (e && e[0] == '0') ? 0 : 1;
 }
 
 // ---- fused render -------------------------------------------------------------------------------
@@ -2244,7 +2267,7 @@ extern "C" int schw_fp64_peak_probe(schw_handle *h, double *tflops, float *ms_ou
 // ---- step-loop probe (diagnostic) -----------------------------------------------------------------
 // variant: rays per thread * 100 + CTAs per SM requested (106, 105, 203, 204).  Returns kernel ms and the warp-steps run.
 extern "C" int schw_step_probe(schw_handle *h, int variant, int iters, double delta, float *ms, uint64_t *warp_steps,
-                               int *ctas_per_sm, int *regs)
+                               int *ctas_per_sm, int *regs, double *planar_fraction)
 {
     if (!h || !ms || !warp_steps) return fail(SCHW_E_INVALID, "null argument");
     CU(cudaSetDevice(h->device));
@@ -2275,9 +2298,12 @@ extern "C" int schw_step_probe(schw_handle *h, int variant, int iters, double de
     if (occ > want) occ = want;
     const int blocks = h->sm_count * occ;
     double *out = (double *)h->in_c.p;
-    void *args[] = {(void *)&P, (void *)&iters, (void *)&out};
+    int period = 2000, rounds = (iters + period - 1) / period;
+    Counters *ctr = h->ctr;
+    void *args[] = {(void *)&P, (void *)&rounds, (void *)&period, (void *)&out, (void *)&ctr};
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
+        CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
         CU(cudaEventRecord(h->ev0, st));
         CU(cudaLaunchKernel(fn, dim3(blocks), dim3(kBlock), args, 0, st));
         CU(cudaEventRecord(h->ev1, st));
@@ -2287,7 +2313,10 @@ extern "C" int schw_step_probe(schw_handle *h, int variant, int iters, double de
         if (t < best) best = t;
     }
     *ms = best;
-    *warp_steps = (uint64_t)blocks * (kBlock / 32) * (uint64_t)iters;
+    *warp_steps = (uint64_t)blocks * (kBlock / 32) * (uint64_t)rounds * (uint64_t)period;
+    Counters c;
+    CU(cudaMemcpy(&c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost));
+    if (planar_fraction) *planar_fraction = c.warp_iters ? (double)c.planar_iters / (double)c.warp_iters : 0.0;
     if (ctas_per_sm) *ctas_per_sm = occ;
     if (regs) *regs = fa.numRegs;
     return SCHW_OK;

@@ -102,7 +102,8 @@ def load():
     L.schw_last_status.argtypes = [vp]
     L.schw_flat_raytrace.argtypes = [vp, dp, dp, i64, dbl, dbl, dbl, dbl, dbl, i32, i32, vp, i32, i32, vp, vp, i64, i64, dp]
     L.schw_observer_q0.argtypes = [scp, dp]
-    L.schw_step_probe.argtypes = [vp, i32, i32, dbl, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.schw_step_probe.argtypes = [vp, i32, i32, dbl, C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_double)]
     L.schw_dedup_plan_dev.argtypes = [vp, scp, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), vp]
     L.schw_dedup_integrate_dev.argtypes = [vp, scp, i32, vp, vp, vp]
     L.schw_dedup_epilogue_dev.argtypes = [vp, scp, vp, i32, i32, i32, vp, i64, vp, i64, xop, vp, vp, vp]
@@ -262,9 +263,11 @@ class Handle:
 
     def step_probe(self, variant, iters=20000, delta=0.01):
         """The render kernel's loop body alone: dict(ms, warp_steps, ctas_per_sm, regs, rays_per_thread)."""
-        ms, ws, occ, regs = C.c_float(), C.c_uint64(), C.c_int(), C.c_int()
-        _check(self._L.schw_step_probe(self._h, int(variant), int(iters), float(delta), C.byref(ms), C.byref(ws), C.byref(occ), C.byref(regs)))
-        return dict(ms=ms.value, warp_steps=int(ws.value), ctas_per_sm=occ.value, regs=regs.value, rays_per_thread=variant // 100)
+        ms, ws, occ, regs, pf = C.c_float(), C.c_uint64(), C.c_int(), C.c_int(), C.c_double()
+        _check(self._L.schw_step_probe(self._h, int(variant), int(iters), float(delta), C.byref(ms), C.byref(ws), C.byref(occ),
+                                       C.byref(regs), C.byref(pf)))
+        return dict(ms=ms.value, warp_steps=int(ws.value), ctas_per_sm=occ.value, regs=regs.value, rays_per_thread=variant // 100,
+                    planar_fraction=pf.value)
 
     def math_probe(self, x):
         x = np.ascontiguousarray(x, np.float64)

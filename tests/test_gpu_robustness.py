@@ -123,3 +123,24 @@ def test_integrate_batch_full_dev_equals_the_host_entry_point(handle):
     fin = handle.integrate_batch(q0s, p0s, k, delta, rs, r_max, omega)
     live = rows_want > k
     assert np.array_equal(fin[live], want[live, k], equal_nan=True)
+
+
+def test_thresholds_a_few_ulps_apart(handle, orc):
+    """r_max within the same high word as the capture radius: no radius passes the integer pre-test of the termination
+    test, so lanes without a ray cannot be parked 'inside' -- every step then takes the exact FP64 test, which must
+    ignore them.  Rays start inside the sliver, outside it, and far away; a mixed warp with empty lanes."""
+    rs = 2.0
+    rcap = 1.1 * rs
+    r_max = rcap * (1 + 3e-9)
+    q0s = np.zeros((45, 4)); p0s = np.zeros((45, 4))
+    q0s[:, 1] = np.where(np.arange(45) % 3 == 0, rcap * (1 + 1e-9), np.where(np.arange(45) % 3 == 1, rcap * (1 - 1e-9), 30.0))
+    q0s[:, 2] = np.pi / 2
+    f = 1 - rs / q0s[:, 1]
+    p0s[:, 1] = np.where(np.arange(45) % 2 == 0, 1e-9, -1e-9) * f; p0s[:, 3] = 1e-9 * q0s[:, 1]
+    p0s[:, 0] = np.sqrt(np.abs(f * p0s[:, 1] ** 2 + p0s[:, 3] ** 2 / q0s[:, 1] ** 2) / np.abs(f)) * np.sign(f)
+    for steps in (0, 1, 7, 400):
+        out, ns = handle.integrate_batch(q0s, p0s, steps, 0.01, rs, r_max, 1.0, want_steps=True)
+        ref, ns_ref = orc.integrate_batch(q0s, p0s, steps, 0.01, rs, r_max, 1.0)
+        assert np.array_equal(ns, ns_ref), steps
+        assert np.allclose(out, ref, rtol=1e-12, atol=1e-12, equal_nan=True), steps
+    assert set(np.unique(ns)) >= {0, 400}

@@ -127,15 +127,28 @@ def test_planar_step_leaves_and_rejoins_the_general_flow(model):
             assert 0 < r["planar"] < r["steps"], (name, r)
 
 
+def hi_rcap_of(buf):
+    import struct
+    return struct.unpack_from("8i", buf, 112)[4]
+
+
+def hi_rmax_of(buf):
+    import struct
+    return struct.unpack_from("8i", buf, 112)[5]
+
+
 def test_thresholds_satisfy_their_derivation(model):
     """(R1)-(R3) of csrc/schw_device.cuh 'Planar steps' from the numbers the library hands to the kernels."""
     import struct
     params, _ = model
     for steps, delta, mass, r_obs, r_max, omega in SCENES + [(10, 0.5, 1.0, 30.0, 31.0, 1.0), (10, 1e-4, 1.0, 30.0, 31.0, 50.0)]:
         buf = params(steps, delta, 2.0 * mass, r_max, omega).raw
-        d = struct.unpack_from("12d", buf, 0)
-        i = struct.unpack_from("8i", buf, 96)
-        h, h_rs, dl, d_rs, mg, mhs, hcB, hcA, rs, zero_hs, rcap, rmax = d
+        d = struct.unpack_from("14d", buf, 0)
+        i = struct.unpack_from("8i", buf, 112)
+        h, h_rs, dl, d_rs, mg, mhs, hcB, hcA, rs, zero_hs, rcap, rmax, park_r, _ = d
+        # lanes without a ray are parked where the termination pre-test lets them be (strictly between the thresholds' high words)
+        hiw = lambda x: struct.unpack("<ii", struct.pack("<d", x))[1]
+        assert rcap < park_r < rmax and hi_rcap_of(buf) < hiw(park_r) < hi_rmax_of(buf)
         ph_hi, r_hi, pp_hi, enable, hi_rcap, hi_rmax, nsteps, _ = i
         assert (h, dl, rs, rmax, nsteps) == (0.5 * delta, delta, 2.0 * mass, r_max, steps)
         assert hcA == delta * 6.123233995736766e-17 and hcB == h * 6.123233995736766e-17 and zero_hs == 0.0
@@ -165,8 +178,8 @@ def test_random_parameter_sets_and_near_threshold_rays(model):
         r_obs = 2.0 * mass * rng.uniform(3.0, 40.0)
         r_max = r_obs * rng.uniform(1.01, 1.5)
         P = params(2500, delta, 2.0 * mass, r_max, omega)
-        enable, = struct.unpack_from("i", P.raw, 96 + 12)
-        T = struct.unpack("<d", struct.pack("<II", 0, struct.unpack_from("i", P.raw, 96)[0] & 0xffffffff))[0] if enable else 1e-15
+        enable, = struct.unpack_from("i", P.raw, 112 + 12)
+        T = struct.unpack("<d", struct.pack("<II", 0, struct.unpack_from("i", P.raw, 112)[0] & 0xffffffff))[0] if enable else 1e-15
         for _ in range(6):
             alpha = np.deg2rad(rng.uniform(0.0, 60.0))
             pth = rng.choice([-0.0, 0.0, 1.0, -1.0]) * T * 10.0 ** rng.uniform(-3, 2)

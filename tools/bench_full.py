@@ -21,7 +21,7 @@ import schw_b200  # noqa: E402
 import torch  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--rays", type=int, default=262144)
+ap.add_argument("--rays", type=int, default=227328, help="default: two full waves of 148 SMs x 6 CTAs x 128 threads")
 ap.add_argument("--steps", type=int, default=512)
 ap.add_argument("--delta", type=float, default=0.01)
 ap.add_argument("--kind", default="camera", choices=["camera", "general"])
@@ -36,7 +36,7 @@ if a.kind == "camera":          # equatorial camera rays of the default scene (u
     al = np.deg2rad(rng.uniform(12.0, 50.0, n)); r0 = np.full(n, 30.0); th0 = np.full(n, np.pi / 2)
     pr = -np.cos(al) * np.sqrt(1 - 2 / r0); pth = -0.0 * r0; pph = np.sin(al) * r0
 else:                           # tilted rays with real polar motion: the general flows, three sincos per step
-    r0 = rng.uniform(20, 40, n); th0 = rng.uniform(0.6, np.pi - 0.6, n)
+    r0 = rng.uniform(40, 60, n); th0 = rng.uniform(0.6, np.pi - 0.6, n)
     al = np.deg2rad(rng.uniform(15, 55, n)); be = rng.uniform(-np.pi, np.pi, n)
     pr = -np.cos(al) * np.sqrt(1 - 2 / r0); pth = np.sin(al) * np.sin(be) * r0; pph = np.sin(al) * np.cos(be) * r0 * np.sin(th0)
 f = 1 - 2 / r0
