@@ -368,6 +368,144 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
 }
 
 // ---------------------------------------------------------------------------------------------
+// The render kernel for whole tiles, R rays per thread (the shipped render path when the observer lies in the
+// equatorial plane, i.e. for the reference's only camera).
+//
+// A warp takes R consecutive 32-pixel tiles of the (longest-first) queue at a time and integrates their 32 R rays in
+// lock step -- lane l carries pixel l of each of the R tiles -- until the last of them has ended, then classifies them
+// all and takes the next R tiles.  Neighbouring pixels, and neighbouring tiles of the sorted queue, need almost the same
+// number of steps, so the warp stays full until it retires.  Compared with persistent_rays (per-lane refill):
+//   * all rays of a warp start together: ONE step counter per warp, no per-lane bookkeeping in the loop, the service
+//     (epilogue + prologue, ~1500 instructions per ray) runs with all 32 lanes instead of a few;
+//   * R independent geodesics per thread share the loop control, the four votes, the branches and the constant loads of
+//     a loop body (paid once per R ray-steps) and hide each other's FP64 dependency latency.
+// Same arithmetic per ray (step_BCBA_planar_n<R> issues exactly the instructions of step_BCBA_planar for each ray), so
+// the outputs are bit-identical to persistent_rays' (tests/test_gpu_planar.py, tools/ab_tile.py).
+// ---------------------------------------------------------------------------------------------
+#ifndef SCHW_TILE_RAYS
+#define SCHW_TILE_RAYS 2
+#endif
+#ifndef SCHW_TILE_MINBLOCKS
+#define SCHW_TILE_MINBLOCKS 4
+#endif
+template <int R>
+__global__ void __launch_bounds__(kBlock, R == 1 ? SCHW_MINBLOCKS : SCHW_TILE_MINBLOCKS)
+persistent_tiles(const __grid_constant__ RenderJob job, const __grid_constant__ StepParams P, Counters *ctr)
+{
+    __shared__ double2 s_slot[R * kBlock];        // (alpha0, beta) per ray, for its epilogue
+    __shared__ double2 s_fin[R * 2 * kBlock];     // final (t,r),(theta,phi) of an ended ray
+    __shared__ double2 s_stage[4 * kBlock];       // (q0, p0) between load() and the state registers
+    __shared__ int s_n[R * kBlock];               // steps taken by an ended ray
+    __shared__ Memo2 s_memo[R * kBlock];
+    __shared__ unsigned long long s_total;
+    if (threadIdx.x == 0) s_total = 0ull;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u;
+    RayState S[R];
+    int kk[R], pp_hi[R];
+    bool active[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) s_memo[r * kBlock + threadIdx.x].init(P.delta, P.h);
+    int it = 0, n_general = 0;
+    unsigned long long mine = 0ull;               // steps integrated by this thread's rays
+    bool inputs_ready = job.ready_flag() == nullptr;
+#pragma unroll
+    for (int r = 0; r < R; ++r) kk[r] = -1;
+    while (true) {
+        // ---- epilogue of the tiles integrated in the previous iteration: rotate back, classify, texel (all lanes together).
+        //      (At the TOP of the loop, like persistent_rays' service: with the divergent per-ray code right in front of the
+        //       loop's back edge the compiler no longer proves that the votes of the step loop are reached convergently.)
+        if (!inputs_ready && __any_sync(kFull, kk[0] >= 0)) {       // (tile 0 of a group is never empty when the group exists)
+            wait_flag_warp(job.ready_flag(), job.err_word());         // the first texel lookup of this warp
+            inputs_ready = true;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (kk[r] >= 0) {
+                const double2 a = s_fin[(2 * r) * kBlock + threadIdx.x], b = s_fin[(2 * r + 1) * kBlock + threadIdx.x];
+                const int ns = s_n[r * kBlock + threadIdx.x];
+                job.store(kk[r], a.x, a.y, b.x, b.y, ns, !(a.y == a.y), s_slot[r * kBlock + threadIdx.x]);
+                mine += (unsigned long long)ns;
+            }
+        }
+        // ---- R tiles for the warp ----
+        long long base = 0;
+        if (lane == 0) base = (long long)atomicAdd(&ctr->next, (unsigned long long)(32 * R));
+        base = __shfl_sync(kFull, base, 0);
+        // (the exit test is a vote so that the compiler can see it is warp-uniform: every *_sync of the step loop must be
+        //  reached provably convergently, tests/test_abi_symbols.py::test_step_loop_sass_budget)
+        if (__all_sync(kFull, base >= job.queue_len())) break;
+        // ---- prologue: camera ray, initial conditions, leading A(d/2) ----
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const long long q = base + 32 * r + lane;
+            kk[r] = q < job.queue_len() ? (int)job.resolve(q) : -1;
+            active[r] = false;
+            if (kk[r] >= 0) {
+                job.load(kk[r], &s_stage[threadIdx.x], s_slot[r * kBlock + threadIdx.x]);
+                const double2 qa = s_stage[threadIdx.x], qb = s_stage[kBlock + threadIdx.x];
+                const double2 pa = s_stage[2 * kBlock + threadIdx.x], pb = s_stage[3 * kBlock + threadIdx.x];
+                const double q0[4] = {qa.x, qa.y, qb.x, qb.y}, p0[4] = {pa.x, pa.y, pb.x, pb.y};
+                init_state(S[r], q0, p0);
+                if (P.steps <= 0 || terminated(S[r].q1r, P)) {           // cuda_geodesic.py:598: the test precedes the first step
+                    s_fin[(2 * r) * kBlock + threadIdx.x] = make_double2(S[r].q1t, S[r].q1r);
+                    s_fin[(2 * r + 1) * kBlock + threadIdx.x] = make_double2(S[r].q1h, S[r].q1p);
+                    s_n[r * kBlock + threadIdx.x] = 0;
+                    park(S[r], P);
+                } else {
+                    flow_A<false>(S[r], P.h, P.h_rs, P.rs, s_memo[r * kBlock + threadIdx.x]);
+                    active[r] = true;
+                }
+            } else {
+                park(S[r], P);
+            }
+            pp_hi[r] = active[r] ? P.pl_pp_hi : 0;
+        }
+        // ---- integrate the 32 R rays in lock step: n = steps taken so far by every ray still running ----
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) any |= active[r];
+        int n = 0, tok = 0;
+        if (__any_sync(kFull, any)) {
+            while (true) {
+                bool next = false;
+                step_BCBA_planar_n<R>(S, P, &s_memo[threadIdx.x], kBlock, pp_hi, tok, next, n_general);
+                ++n; ++it;
+                const bool cap = n >= P.steps;                                   // (warp-uniform)
+                bool maybe = false;
+#pragma unroll
+                for (int r = 0; r < R; ++r) maybe |= maybe_finished(S[r].q1r, P);   // (parked lanes pass the pre-test: P.park_r)
+                tok = __all_sync(kFull, next & !maybe) && !cap;
+                if (!tok && (cap || __any_sync(kFull, maybe))) {
+                    bool left = false;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (active[r] && (cap || finished_or_nan(S[r].q1r, P))) {
+                            s_fin[(2 * r) * kBlock + threadIdx.x] = make_double2(S[r].q1t, S[r].q1r);
+                            s_fin[(2 * r + 1) * kBlock + threadIdx.x] = make_double2(S[r].q1h, S[r].q1p);
+                            s_n[r * kBlock + threadIdx.x] = n;
+                            active[r] = false; pp_hi[r] = 0;
+                            park(S[r], P);
+                        }
+                        left |= active[r];
+                    }
+                    if (!__any_sync(kFull, left)) break;
+                }
+            }
+        }
+    }
+    // (one atomic per thread, after the loop: a lane-conditional atomic in front of the loop's back edge would cost the
+    //  compiler its proof that the votes of the next iteration are reached convergently)
+    atomicAdd(&s_total, mine);
+    if (lane == 0 && it) {
+        atomicAdd(&ctr->warp_iters, (unsigned long long)it * R);      // loop bodies per RAY slot, as persistent_rays counts them
+        atomicAdd(&ctr->planar_iters, (unsigned long long)(it - n_general) * R);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_total) atomicAdd(&ctr->total_steps, s_total);
+}
+
+// ---------------------------------------------------------------------------------------------
 // integrate_batch_full: fantasy_integrate_batch_ord2_full, cuda_geodesic.py:604-625.
 // Row `step` of a ray holds q1 *before* the termination test of that step (the terminal state is stored, the state
 // after the last of `steps` steps is not); rows after a ray's last stored row are left untouched (the host entry point
@@ -926,6 +1064,7 @@ struct schw_handle {
     int launches = 0;
     Counters *ctr = nullptr;
     int occ_render[3] = {0, 0, 0}, occ_batch[3] = {0, 0, 0};   // filled on first use, see launch_persistent
+    int occ_tiles[3] = {0, 0, 0};                               // persistent_tiles<R>, index R
     // grow-only scratch
     DevBuf in_a, in_b, in_c, tex, rgb, cls, fq, ic, hit, texel, nsteps, traj, rows, order;
     DevBuf dd_keys, dd_keys2, dd_pix, dd_pix2, dd_head, dd_uid, dd_map, dd_tmp, dd_q0, dd_p0, dd_fq, dd_ns;   // de-duplication
@@ -1333,6 +1472,37 @@ static int launch_persistent(schw_handle *h, const Job &job, const StepParams &P
     return launch_variant<Job, true, true>(h, job, P, occ[2], st);
 }
 
+// The whole-tile render kernel (persistent_tiles<R>): R rays per thread; SCHW_TILE_RAYS=1|2 at run time (A/B measurements).
+static int tile_rays()
+{
+    const char *e = getenv("SCHW_TILE_RAYS");
+    if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+    return SCHW_TILE_RAYS;
+}
+template <int R>
+static int launch_tiles_variant(schw_handle *h, const RenderJob &job, const StepParams &P, cudaStream_t st)
+{
+    auto kern = persistent_tiles<R>;
+    int &occ = h->occ_tiles[R];
+    if (occ == 0) {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, 0));
+        if (occ < 1) return fail(SCHW_E_CUDA, "kernel does not fit on an SM");
+    }
+    const long long want_blocks = (job.qlen + (long long)kBlock * R - 1) / ((long long)kBlock * R);
+    long long grid = (long long)h->sm_count * occ;
+    if (grid > want_blocks) grid = want_blocks;
+    kern<<<(unsigned)grid, kBlock, 0, st>>>(job, P, h->ctr);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return SCHW_OK;
+}
+static int launch_tiles(schw_handle *h, const RenderJob &job, const StepParams &P, cudaStream_t st)
+{
+    CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
+    if (job.n <= 0) return SCHW_OK;
+    return tile_rays() == 1 ? launch_tiles_variant<1>(h, job, P, st) : launch_tiles_variant<2>(h, job, P, st);
+}
+
 // ---- integrate_batch ----------------------------------------------------------------------------
 static int integrate_batch_impl(schw_handle *h, const double *d_q0s, const double *d_p0s, int64_t n,
                                 int64_t steps, double delta, double rs, double r_max, double omega,
@@ -1684,10 +1854,13 @@ static bool lpt_order_enabled() { return env_switch_on("SCHW_LPT_ORDER"); }
 // Refill policy of the render queue (RenderJob::tile_mode): whole tiles by default -- measured faster at every frame size
 // (profiles/r02_ab_tile.json: 400x400 7.12 -> 6.81 ms, a 1/8 shard of the 4K frame 39.26 -> 39.02 ms, the 4K frame
 // 308.7 -> 306.1 ms, same output bits); SCHW_TILE_MODE=0 selects the per-lane refill (A/B measurements).
+// SCHW_TILE_MODE: 0 = per-lane refill (persistent_rays), 1 = whole tiles inside persistent_rays, 2 (default) = the
+// whole-tile kernel persistent_tiles<R>.
 static int tile_mode_for(const schw_handle *, long long)
 {
     const char *e = getenv("SCHW_TILE_MODE");
-    return (e && e[0] == '0') ? 0 : 1;
+    if (e && (e[0] == '0' || e[0] == '1')) return e[0] - '0';
+    return 2;
 }
 
 // ---- fused render -------------------------------------------------------------------------------
@@ -1735,7 +1908,9 @@ extern "C" int schw_render_dev_pitched(schw_handle *h, const schw_scene *scene, 
         job.tile_mode = tile_mode_for(h, n);
     }
     begin_timed(h, st);
-    rc = launch_persistent(h, job, P, h->occ_render, st);
+    // equatorial observer (every ray planar) + whole tiles: the tile kernel; otherwise the per-lane-refill kernel
+    if (job.tile_mode == 2 && P.pl_enable && trig_memo_enabled()) rc = launch_tiles(h, job, P, st);
+    else rc = launch_persistent(h, job, P, h->occ_render, st);
     end_timed(h, st);
     return rc;
 }

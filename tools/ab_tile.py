@@ -29,21 +29,23 @@ for (h, w, stride) in ((400, 400, 1), (1080, 1920, 1), (2160, 3840, 8), (2160, 3
     sc = schw_b200.make_scene(height=h, width=w)
     row = {"height": h, "width": w, "rows": f"0::{stride}"}
     outs = {}
-    for mode in ("0", "1"):
+    for mode, rays in (("0", "1"), ("1", "1"), ("2", "1"), ("2", "2")):
         os.environ["SCHW_TILE_MODE"] = mode
+        os.environ["SCHW_TILE_RAYS"] = rays
+        mode = {"0": "lane_refill", "1": "tiles_in_lane_kernel"}.get(mode, f"tile_kernel_r{rays}")
         best = 1e30
         for _ in range(a.reps):
             out = hd.render(sc, tex, 0, h, stride, extras=(h <= 1080))
             best = min(best, hd.last_kernel_ms()[0])
         steps, warp_iters, planar = hd.last_counters()
         outs[mode] = out
-        row[f"tile{mode}_ms"] = best
-        row[f"tile{mode}_lane_utilisation"] = steps / (32.0 * warp_iters)
+        row[f"{mode}_ms"] = best
+        row[f"{mode}_lane_utilisation"] = steps / (32.0 * warp_iters)
         row["steps"] = steps
-    row["identical"] = all(np.array_equal(outs["0"][k], outs["1"][k], equal_nan=(k == "final_q")) for k in outs["0"])
-    row["speedup_of_whole_tiles"] = row["tile0_ms"] / row["tile1_ms"]
+    row["identical"] = all(np.array_equal(outs["lane_refill"][k], o[k], equal_nan=(k == "final_q")) for o in outs.values() for k in o)
+    row["speedup_tile_kernel_r2_over_lane_refill"] = row["lane_refill_ms"] / row["tile_kernel_r2_ms"]
     res.append(row)
     print(json.dumps(row), flush=True)
-os.environ.pop("SCHW_TILE_MODE", None)
+os.environ.pop("SCHW_TILE_MODE", None); os.environ.pop("SCHW_TILE_RAYS", None)
 if a.out:
     json.dump(res, open(a.out, "w"), indent=1)

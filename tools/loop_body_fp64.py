@@ -23,7 +23,10 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "schwarzchild-einsteinpy-raytracing_b200")
 FP64 = ("DFMA", "DMUL", "DADD", "DSETP")
-KERNEL = "persistent_raysINS_9RenderJobELb1ELb1"
+# (kernel name substring, call marker in schw_kernels.cu, rays per thread): the shipped render kernel first
+KERNELS = (("persistent_tilesILi2E", "step_BCBA_planar_n<R>(", 2),
+           ("persistent_tilesILi1E", "step_BCBA_planar_n<R>(", 1),
+           ("persistent_raysINS_9RenderJobELb1ELb1", "step_BCBA_planar(", 1))
 
 
 def csrc_sha():
@@ -33,19 +36,9 @@ def csrc_sha():
     return hsh.hexdigest()[:16]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--lib", default=os.path.join(PKG, "lib", "libschw_b200.so"))
-    ap.add_argument("--out", default=os.path.join(PKG, "lib", "loop_body.json"))
-    a = ap.parse_args()
-    ksrc = open(os.path.join(PKG, "csrc", "schw_kernels.cu")).read().splitlines()
-    dsrc = open(os.path.join(PKG, "csrc", "schw_device.cuh")).read().splitlines()
-    call_lines = [i + 1 for i, l in enumerate(ksrc) if "step_BCBA_planar(" in l and "//" not in l.split("step_BCBA_planar(")[0]]
-    assert call_lines, "no call of step_BCBA_planar in schw_kernels.cu"      # (one per kernel that uses it; KERNEL selects)
-    with tempfile.TemporaryDirectory() as d:
-        subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(a.lib)], cwd=d, stdout=subprocess.DEVNULL)
-        cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-        txt = subprocess.run(["nvdisasm", "-gi", "-c", cubin], cwd=d, capture_output=True, text=True).stdout
+def analyse(txt, ksrc, dsrc, kernel, marker, rays):
+    call_lines = [i + 1 for i, l in enumerate(ksrc) if marker in l and "//" not in l.split(marker)[0]]
+    assert call_lines, f"no call of {marker} in schw_kernels.cu"
     inside = False
     chain = []
     fresh = True            # the next //## line starts a new chain
@@ -54,7 +47,7 @@ def main():
     for line in txt.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+?),", line)
         if m:
-            inside = KERNEL in m.group(1)
+            inside = kernel in m.group(1)
             continue
         if not inside:
             continue
@@ -73,7 +66,7 @@ def main():
         hits = [c for c in chain if c[0] == "schw_kernels.cu" and c[1] in call_lines]
         if not hits:
             continue
-        # the call site inside step_BCBA_planar = the chain entry right below the kernel's call
+        # the call site inside the step function = the chain entry right below the kernel's call
         k = chain.index(hits[0])
         site = chain[k - 1] if k > 0 else None
         text = dsrc[site[1] - 1] if site and site[0] == "schw_device.cuh" else ""
@@ -82,7 +75,8 @@ def main():
             cat = "memo_miss"          # re-evaluation of a memoised trig factor: only when an angle's bits changed
         elif "flow_tail_planar(" in text or "mix_planar(" in text:
             cat = "fast_only"
-        elif "flow_tail(" in text or "memo_refresh(" in text or re.search(r"if \(!v\d\) mix\(", text) or "++n_general" in text:
+        elif ("flow_tail(" in text or "memo_refresh(" in text or re.search(r"if \(!v\d\) mix\(", text) or "++n_general" in text
+              or re.search(r"mix\(S\[r\]\.q1h", text)):
             cat = "general_only"
         else:
             cat = "common"
@@ -90,22 +84,41 @@ def main():
         cat_all[cat] += 1
         if op in FP64:
             cat_fp[cat] += 1
-    assert cat_fp["common"] > 0, "no instruction of the loop body found: did the kernel or the step function change its name?"
-    out = {
-        "csrc_sha": csrc_sha(), "kernel": KERNEL,
-        "fp64_per_body_fast_path": cat_fp["common"] + cat_fp["fast_only"],
-        "fp64_per_body_general": cat_fp["common"] + cat_fp["general_only"],
-        "fp64_per_memo_miss_all_three_flows": cat_fp["memo_miss"],
+    assert cat_fp["common"] > 0, f"no instruction of the loop body of {kernel} found: did the kernel or the step function change its name?"
+    return {
+        "kernel": kernel, "rays_per_thread": rays,
+        # per ray-step (a loop body of an R-ray kernel advances R rays; Counters::warp_iters counts ray slots)
+        "fp64_per_body_fast_path": (cat_fp["common"] + cat_fp["fast_only"]) / rays,
+        "fp64_per_body_general": (cat_fp["common"] + cat_fp["general_only"]) / rays,
+        "fp64_per_memo_miss_all_three_flows": cat_fp["memo_miss"] / rays,
         # BRA.DIV = the compiler could not prove that a *_sync vote is reached convergently and emitted divergence handling
-        # around it (a 13 % slowdown of the step loop when it happened); must stay 0 (tests/test_host_logic.py)
+        # around it (a 13 % slowdown of the step loop when it happened); must stay 0 (tests/test_abi_symbols.py)
         "bra_div_in_kernel": bra_div,
         "detail": {"fp64": dict(cat_fp), "static_instructions": dict(cat_all)},
-        "how": "nvdisasm -gi of the built library: instructions whose inline chain passes through the kernel's call of "
-               "step_BCBA_planar, split by call site (tools/loop_body_fp64.py).  'general' = all three flows and the mixing off "
-               "the fast path with the trig memo hitting; the memo-miss re-evaluation (sincos + reciprocal, only when an angle's "
-               "bits changed) is listed separately and not counted by bench.py.  The loop control outside step_BCBA_planar "
-               "(termination pre-test, counters) holds no FP64-pipe instruction",
     }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lib", default=os.path.join(PKG, "lib", "libschw_b200.so"))
+    ap.add_argument("--out", default=os.path.join(PKG, "lib", "loop_body.json"))
+    a = ap.parse_args()
+    ksrc = open(os.path.join(PKG, "csrc", "schw_kernels.cu")).read().splitlines()
+    dsrc = open(os.path.join(PKG, "csrc", "schw_device.cuh")).read().splitlines()
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(a.lib)], cwd=d, stdout=subprocess.DEVNULL)
+        cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
+        txt = subprocess.run(["nvdisasm", "-gi", "-c", cubin], cwd=d, capture_output=True, text=True).stdout
+    per_kernel = [analyse(txt, ksrc, dsrc, *k) for k in KERNELS]
+    out = dict(per_kernel[0])                 # the shipped render kernel at the top level (what bench.py reads)
+    out.update({
+        "csrc_sha": csrc_sha(), "kernels": per_kernel,
+        "how": "nvdisasm -gi of the built library: instructions whose inline chain passes through the kernel's call of the step "
+               "function (step_BCBA_planar / step_BCBA_planar_n<R>), split by call site (tools/loop_body_fp64.py), per ray-step.  "
+               "'general' = all three flows and the mixing off the fast path with the trig memo hitting; the memo-miss "
+               "re-evaluation (sincos + reciprocal, only when an angle's bits changed) is listed separately and not counted by "
+               "bench.py.  The loop control outside the step function (termination pre-test, counters) holds no FP64-pipe instruction",
+    })
     json.dump(out, open(a.out, "w"), indent=1)
     print(json.dumps(out))
 
