@@ -396,7 +396,7 @@ def main():
                 "peak_source": f"FP64 pipe: {info['sm_count']} SMs x 64 lanes x 2 (FMA) x {sm_mhz:.0f} MHz (SM clock sampled under load); "
                                "MEASURED_PEAKS.json has no FP64 entry; a pure register-resident DFMA stream measured in this run "
                                "(schw_fp64_peak_probe) is dfma_probe_tflops",
-                "dfma_probe_tflops": probe_tflops, "kernel": "persistent_rays<RenderJob>", "kernel_ms": kern_ms,
+                "dfma_probe_tflops": probe_tflops, "kernel": body.get("kernel", "render kernel") if body else "render kernel", "kernel_ms": kern_ms,
                 "traffic": ncu.get("dram_bytes_per_launch"), "traffic_note": ncu_stale or ncu.get("source"),
                 "algorithmic_bytes_per_launch": 7 * h * w,
                 "lane_utilisation": steps_per_frame_local / (32.0 * warp_iters) if warp_iters else None,

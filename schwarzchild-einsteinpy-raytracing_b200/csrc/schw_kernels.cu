@@ -388,10 +388,11 @@ persistent_rays(const __grid_constant__ Job job, const __grid_constant__ StepPar
 #ifndef SCHW_TILE_MINBLOCKS
 #define SCHW_TILE_MINBLOCKS 4
 #endif
-template <int R>
+template <class Job, int R>
 __global__ void __launch_bounds__(kBlock, R == 1 ? SCHW_MINBLOCKS : SCHW_TILE_MINBLOCKS)
-persistent_tiles(const __grid_constant__ RenderJob job, const __grid_constant__ StepParams P, Counters *ctr)
+persistent_tiles(const __grid_constant__ Job job, const __grid_constant__ StepParams P, Counters *ctr)
 {
+    if (job.skip()) return;                       // (grid-uniform)
     __shared__ double2 s_slot[R * kBlock];        // (alpha0, beta) per ray, for its epilogue
     __shared__ double2 s_fin[R * 2 * kBlock];     // final (t,r),(theta,phi) of an ended ray
     __shared__ double2 s_stage[4 * kBlock];       // (q0, p0) between load() and the state registers
@@ -1472,23 +1473,28 @@ static int launch_persistent(schw_handle *h, const Job &job, const StepParams &P
     return launch_variant<Job, true, true>(h, job, P, occ[2], st);
 }
 
-// The whole-tile render kernel (persistent_tiles<R>): R rays per thread; SCHW_TILE_RAYS=1|2 at run time (A/B measurements).
-static int tile_rays()
+// The whole-tile kernel (persistent_tiles<Job, R>), R rays per thread.  Two rays per thread (4 CTAs/SM) are faster once a
+// warp gets many tiles -- 4K frame 297.8 -> 292.4 ms, 1080p 75.5 -> 74.3 ms -- while one ray per thread (6 CTAs/SM: smaller
+// units of work) ends a short launch sooner -- a 1/8 shard of the 4K frame 37.8 vs 38.0 ms, 400x400 6.85 vs 7.11 ms
+// (profiles/r02_ab_tile.json).  SCHW_TILE_RAYS=1|2 forces one (A/B measurements).
+static int tile_rays(long long qlen)
 {
     const char *e = getenv("SCHW_TILE_RAYS");
     if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
-    return SCHW_TILE_RAYS;
+    return qlen / 32 >= 40000 ? SCHW_TILE_RAYS : 1;
 }
-template <int R>
-static int launch_tiles_variant(schw_handle *h, const RenderJob &job, const StepParams &P, cudaStream_t st)
+static int tile_mode_for(const schw_handle *, long long);
+
+template <class Job, int R>
+static int launch_tiles_variant(schw_handle *h, const Job &job, long long qlen, const StepParams &P, cudaStream_t st)
 {
-    auto kern = persistent_tiles<R>;
-    int &occ = h->occ_tiles[R];
+    auto kern = persistent_tiles<Job, R>;
+    int &occ = h->occ_tiles[R];                   // (RenderJob and BatchJob instances use the same registers and shared memory)
     if (occ == 0) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, 0));
         if (occ < 1) return fail(SCHW_E_CUDA, "kernel does not fit on an SM");
     }
-    const long long want_blocks = (job.qlen + (long long)kBlock * R - 1) / ((long long)kBlock * R);
+    const long long want_blocks = (qlen + (long long)kBlock * R - 1) / ((long long)kBlock * R);
     long long grid = (long long)h->sm_count * occ;
     if (grid > want_blocks) grid = want_blocks;
     kern<<<(unsigned)grid, kBlock, 0, st>>>(job, P, h->ctr);
@@ -1496,18 +1502,21 @@ static int launch_tiles_variant(schw_handle *h, const RenderJob &job, const Step
     CU(cudaGetLastError());
     return SCHW_OK;
 }
-static int launch_tiles(schw_handle *h, const RenderJob &job, const StepParams &P, cudaStream_t st)
+template <class Job>
+static int launch_tiles(schw_handle *h, const Job &job, long long qlen, const StepParams &P, cudaStream_t st, bool reset_counters = true)
 {
-    CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
+    if (reset_counters) CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
     if (job.n <= 0) return SCHW_OK;
-    return tile_rays() == 1 ? launch_tiles_variant<1>(h, job, P, st) : launch_tiles_variant<2>(h, job, P, st);
+    return tile_rays(qlen) == 1 ? launch_tiles_variant<Job, 1>(h, job, qlen, P, st) : launch_tiles_variant<Job, 2>(h, job, qlen, P, st);
 }
 
 // ---- integrate_batch ----------------------------------------------------------------------------
 static int integrate_batch_impl(schw_handle *h, const double *d_q0s, const double *d_p0s, int64_t n,
                                 int64_t steps, double delta, double rs, double r_max, double omega,
-                                double *d_out_qs, int32_t *d_out_steps, void *cuda_stream)
+                                double *d_out_qs, int32_t *d_out_steps, void *cuda_stream, bool coherent = false)
 {
+    // coherent: neighbouring rays of the batch need about the same number of steps (the distinct camera rays of a
+    // de-duplicated frame, in order of camera angle), so planar batches go to the whole-tile kernel
     if (!h) return fail(SCHW_E_INVALID, "null handle");
     if (n < 0 || n > 0x7fffffffLL) return fail(SCHW_E_INVALID, "n must be in [0, 2^31-1]");
     if (n > 0 && (!d_q0s || !d_p0s || !d_out_qs)) return fail(SCHW_E_INVALID, "null array");
@@ -1526,7 +1535,8 @@ static int integrate_batch_impl(schw_handle *h, const double *d_q0s, const doubl
         CU(cudaGetLastError());
         job.select = &h->ctr->batch_planar;
         job.want = 1;
-        rc = launch_persistent(h, job, P, h->occ_batch, st, false);
+        if (coherent && tile_mode_for(h, n) == 2) rc = launch_tiles(h, job, (long long)n, P, st, false);
+        else rc = launch_persistent(h, job, P, h->occ_batch, st, false);
         if (rc) return rc;
         job.want = 0;
         P.pl_enable = 0;
@@ -1909,7 +1919,7 @@ extern "C" int schw_render_dev_pitched(schw_handle *h, const schw_scene *scene, 
     }
     begin_timed(h, st);
     // equatorial observer (every ray planar) + whole tiles: the tile kernel; otherwise the per-lane-refill kernel
-    if (job.tile_mode == 2 && P.pl_enable && trig_memo_enabled()) rc = launch_tiles(h, job, P, st);
+    if (job.tile_mode == 2 && P.pl_enable && trig_memo_enabled()) rc = launch_tiles(h, job, job.qlen, P, st);
     else rc = launch_persistent(h, job, P, h->occ_render, st);
     end_timed(h, st);
     return rc;
@@ -2063,7 +2073,7 @@ static int dedup_integrate(schw_handle *h, const schw_scene *scene, int rank, do
     const size_t first = (size_t)rank * chunk;
     return integrate_batch_impl(h, (const double *)h->dd_q0.p + 4 * first, (const double *)h->dd_p0.p + 4 * first, count,
                                 scene->steps, scene->delta, 2.0 * scene->mass, scene->r_max, scene->omega,
-                                d_fq_all + 4 * first, d_ns_all + first, st);
+                                d_fq_all + 4 * first, d_ns_all + first, st, /*coherent=*/true);
 }
 
 // Stage 3.  Per-pixel epilogue of the rows of THIS call (a subset of the plan's rows) from the distinct rays' final states.

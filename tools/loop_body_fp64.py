@@ -24,8 +24,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "schwarzchild-einsteinpy-raytracing_b200")
 FP64 = ("DFMA", "DMUL", "DADD", "DSETP")
 # (kernel name substring, call marker in schw_kernels.cu, rays per thread): the shipped render kernel first
-KERNELS = (("persistent_tilesILi2E", "step_BCBA_planar_n<R>(", 2),
-           ("persistent_tilesILi1E", "step_BCBA_planar_n<R>(", 1),
+KERNELS = (("persistent_tilesINS_9RenderJobELi2E", "step_BCBA_planar_n<R>(", 2),
+           ("persistent_tilesINS_9RenderJobELi1E", "step_BCBA_planar_n<R>(", 1),
            ("persistent_raysINS_9RenderJobELb1ELb1", "step_BCBA_planar(", 1))
 
 
