@@ -527,7 +527,9 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
 {
     if (select && *select != want) return;                 // (grid-uniform) see batch_probe_kernel
     constexpr int kWarps = kBlock / 32;
-    __shared__ double2 s_stage[kWarps][32 * 8];            // per warp: 32 rays x (4 rows x 32 B) = 4 KB, 16-byte pieces
+    constexpr int kPitch = 9;                              // double2 per ray in the staging area: 4 rows x 2 + 1 of padding,
+                                                           // so that lane-strided 16-byte accesses fall into distinct banks
+    __shared__ double2 s_stage[kWarps][32 * kPitch];       // per warp: 32 rays x (4 rows x 32 B)
     __shared__ int s_rows[kBlock];                         // rows stored by the ray of each lane (INT_MAX while it runs)
     __shared__ unsigned long long s_total;
     __shared__ Memo2 s_memo[kPlanar ? kBlock : 1];
@@ -551,22 +553,35 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
     }
     s_rows[threadIdx.x] = active ? 0x7fffffff : 0;
     int pp_hi = active ? P.pl_pp_hi : 0, tok = 0, n_general = 0, it = 0;
-    double2 *stage = s_stage[warp];
+    double2 *const stage = s_stage[warp];
+    double2 *const mine = stage + lane * kPitch;           // this lane's four staged rows
     const int *rows_w = s_rows + (threadIdx.x & ~31);
     // flush geometry of this lane: in store j (0..7) it writes 16-byte piece `piece` of the 128-byte group of the warp's ray
-    // L = 4 j + l3, read from the swizzled staging slot L*8 + (piece ^ (L & 7)), (L & 7) = 4 (j & 1) + l3
+    // L = 4 j + l3
     const int l3 = (int)(lane >> 3), piece = (int)(lane & 7);
     double2 *const dst0 = reinterpret_cast<double2 *>(out_traj + (size_t)(ray0 + l3) * (size_t)P.steps * 4) + piece;
     const size_t dstride = (size_t)4 * (size_t)P.steps * 2;       // double2 units between the rays of store j and store j+1
-    const int sidx0 = l3 * 8 + (piece ^ l3), sidx1 = (4 + l3) * 8 + (piece ^ (4 + l3));
+    const double2 *const src0 = stage + l3 * kPitch + piece;
+    bool all_running = __all_sync(kFull, active);          // (warp-uniform) no ray of the warp has ended yet: full-line flushes
+    bool any_active = __any_sync(kFull, active);           // (warp-uniform)
+    bool quiet = false;                                    // (warp-uniform) no ray can end at the row about to be stored
     bool first = true;
-    for (int step = 0;; ++step) {                          // (warp-uniform trip count)
-        const int slot = step & 3;
-        if (active) {                                      // row `step`: q1 before the test
-            stage[lane * 8 + ((2 * slot) ^ (lane & 7))] = make_double2(S.q1t, S.q1r);
-            stage[lane * 8 + ((2 * slot + 1) ^ (lane & 7))] = make_double2(S.q1h, S.q1p);
-            // integer pre-test on the high word of r (maybe_finished), the exact FP64 test only when it cannot rule the end out
-            if (maybe_finished(S.q1r, P) || step == P.steps - 1) {
+#ifndef SCHW_FULL_UNROLL
+#define SCHW_FULL_UNROLL 1
+#endif
+    // (SCHW_FULL_UNROLL=4 unrolls the four steps of a row group so that the staging offsets and the flush test are
+    //  compile-time constants: measured equal, 0.567 vs 0.562 of the HBM figure, so the rolled loop is kept)
+    for (int base4 = 0; any_active; base4 += SCHW_FULL_UNROLL) {               // (warp-uniform trip count)
+#pragma unroll
+      for (int sub = 0; sub < SCHW_FULL_UNROLL; ++sub) {
+        const int step = base4 + sub;
+        const int slot = SCHW_FULL_UNROLL == 4 ? sub : (step & 3);
+        // row `step`: q1 before the test (parked lanes stage their fixed point: never flushed)
+        mine[2 * slot] = make_double2(S.q1t, S.q1r);
+        mine[2 * slot + 1] = make_double2(S.q1h, S.q1p);
+        if (!quiet || step == P.steps - 1) {
+            // someone may end here: the exact FP64 test, per lane (cuda_geodesic.py:623), then the warp's bookkeeping
+            if (active) {
                 if (terminated(S.q1r, P) || step == P.steps - 1) {
                     active = false; pp_hi = 0;
                     s_rows[threadIdx.x] = step + 1;
@@ -578,23 +593,22 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
                     S.q1t = S.q1h = S.q1p = S.q2t = S.q2r = S.q2h = S.q2p = nanv;
                 }
             }
+            const unsigned am = __ballot_sync(kFull, active);
+            any_active = am != 0u;
+            all_running = all_running && am == kFull;
         }
-        const bool any_active = __any_sync(kFull, active);
         if (slot == 3 || !any_active) {                    // flush rows [step - slot, step] of the warp's 32 rays
             __syncwarp();
             const int base = step - slot;
-            // all four rows of all 32 rays are valid (the usual case): eight unconditional full-line stores
-            if (__all_sync(kFull, slot == 3 && s_rows[threadIdx.x] > step)) {
-                double2 *dst = dst0 + (size_t)base * 2;
+            double2 *dst = dst0 + (size_t)base * 2;
+            if (all_running && slot == 3) {                // all four rows of all 32 rays are valid: eight full-line stores
 #pragma unroll
-                for (int j = 0; j < 8; ++j) __stcs(dst + j * dstride, stage[32 * j + ((j & 1) ? sidx1 - 32 : sidx0)]);
+                for (int j = 0; j < 8; ++j) __stcs(dst + j * dstride, src0[4 * j * kPitch]);
             } else {
 #pragma unroll 1
                 for (int j = 0; j < 8; ++j) {
                     const int L = 4 * j + l3;
-                    const int gstep = base + (piece >> 1);
-                    if ((piece >> 1) <= slot && gstep < rows_w[L])
-                        __stcs(dst0 + (size_t)base * 2 + j * dstride, stage[L * 8 + (piece ^ (L & 7))]);
+                    if ((piece >> 1) <= slot && base + (piece >> 1) < rows_w[L]) __stcs(dst + j * dstride, src0[4 * j * kPitch]);
                 }
             }
             __syncwarp();
@@ -606,12 +620,18 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
         if (kPlanar) {
             bool next = false;
             step_BCBA_planar(S, P, M, pp_hi, tok, next, n_general);
-            tok = __all_sync(kFull, next);
+            // one vote per step: "everybody may start the next step planar and nobody can end at the next row" (integer
+            // pre-test on the high word of r; parked lanes pass it, StepParams::park_r)
+            const bool maybe = maybe_finished(S.q1r, P);
+            tok = __all_sync(kFull, next & !maybe);
+            quiet = tok ? true : (bool)__all_sync(kFull, !maybe);
         } else {
             step_BCB<true>(S, P, M);
             flow_A<true>(S, P.delta, P.d_rs, P.rs, M);
+            quiet = __all_sync(kFull, !maybe_finished(S.q1r, P));
         }
         ++it;
+      }
     }
     if (i < n && out_rows) out_rows[i] = s_rows[threadIdx.x];
     if (lane == 0 && it) {

@@ -65,6 +65,13 @@ for k in (1, steps // 2, steps - 1):
     ref = hd.integrate_batch(q0[idx], p0[idx], k, a.delta, 2.0, 1e6, 1.0)
     got = traj[torch.from_numpy(idx).cuda(), k].cpu().numpy()
     assert np.array_equal(ref, got), k
+# context: what a pure write stream reaches on this box (torch fill of the same buffer, CUDA events)
+fill_best = 1e30
+for r in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); traj.fill_(1.0); e1.record(); torch.cuda.synchronize()
+    fill_best = min(fill_best, e0.elapsed_time(e1))
+fill_gbs = traj.numel() * 8 / (fill_best * 1e-3) / 1e9
 peaks = {}
 try:
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -76,6 +83,7 @@ gbs = rows_written * 32 / (best * 1e-3) / 1e9
 res = {"what": f"integrate_batch_full_dev, {n} {a.kind} rays x {steps} rows, delta {a.delta}: {rows_written * 32 / 2**30:.2f} GiB of trajectory in HBM",
        "kernel_ms": best, "launches": launches, "rows_per_s": rows_written / (best * 1e-3), "steps_per_s": total / (best * 1e-3),
        "algorithmic_bytes": rows_written * 32, "achieved_gb_s": gbs, "hbm_peak_gb_s": hbm, "frac_of_hbm": gbs / hbm,
+       "pure_write_gb_s_torch_fill_same_buffer": fill_gbs, "frac_of_pure_write": gbs / fill_gbs,
        "planar_fast_path_fraction": planar_iters / warp_iters if warp_iters else None,
        "rows_equal_integrate_batch_after_k_steps": True}
 print(json.dumps(res))

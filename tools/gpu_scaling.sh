@@ -4,7 +4,8 @@
 cd "$(dirname "$0")/.."
 TAG=${1:-r01}
 NG=$(nvidia-smi -L | wc -l)
-[ -n "$SKIP_TESTS" ] || timeout 600 python -m pytest tests/test_gpu_multirank.py -q 2>&1 | tail -2
+# the two-rank NCCL tests (gathered frame == single-GPU frame, with and without de-duplication): the log is kept
+[ -n "$SKIP_TESTS" ] || { timeout 900 python -m pytest tests/test_gpu_multirank.py -m gpu -q -rA > gpurun_out/pytest_multirank_${TAG}.log 2>&1; echo "multirank pytest rc=$?" >> gpurun_out/pytest_multirank_${TAG}.log; tail -3 gpurun_out/pytest_multirank_${TAG}.log; }
 for N in 1 2 4 8; do
   [ $N -gt $NG ] && break
   if [ $N -eq 1 ]; then
@@ -18,7 +19,7 @@ for N in 1 2 4 8; do
 import json
 for l in open("gpurun_out/scale_${TAG}_n$N.json"):
     if l.startswith("{"):
-        d = json.loads(l); print($N, d["value"], d["frame_ms"], d["e2e"]["frame_ms"], d["clocks"])
+        d = json.loads(l); print($N, d["value"], d["frame_ms"], d["e2e"]["frame_ms"], d.get("gather_check"), (d.get("dedup_opt_in") or {}).get("frame_ms_e2e"), d["clocks"])
 PY
 done
 if [ $NG -ge 2 ]; then

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn an ncu report of the render kernel into the committed summaries under profiles/ (runs here, no GPU).
 
-    python tools/summarize_ncu.py gpurun_out/prof_r01_final_4k.ncu-rep <steps> <tag>
+    python tools/summarize_ncu.py gpurun_out/prof_r02_render_4k.ncu-rep <steps> <tag> [<summary.json>]
 """
 import collections
 import csv
@@ -13,7 +13,10 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 rep, steps, tag = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+# optional 4th argument: where the summary goes (default profiles/ncu_summary.json = the render kernel's, read by bench.py)
+summary_path = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "profiles", "ncu_summary.json")
 
 
 def page(name):
@@ -50,7 +53,10 @@ fp = sum(byop[k] for k in ("DFMA", "DMUL", "DADD", "DSETP"))
 flops = 2 * thr_by["DFMA"] + thr_by["DMUL"] + thr_by["DADD"]
 stalls = {h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): float(d[h][1])
           for h in raw[0] if "issue_stalled" in h and h.endswith("per_issue_active.ratio")}
+import bench  # noqa: E402  (csrc_sha: the kernel sources this capture was made from -- run right after the capture)
 summ = {
+    "csrc_sha": bench.csrc_sha(),
+    "dram_bytes_read": nbytes("dram__bytes_read.sum"), "dram_bytes_written": nbytes("dram__bytes_write.sum"),
     "source": f"profiles/{tag}_details.csv (ncu --set full --clock-control none, {d['Kernel Name'][1]}, {steps} geodesic steps)",
     "dram_bytes_per_launch": nbytes("dram__bytes_read.sum") + nbytes("dram__bytes_write.sum"),
     "fp64_pipe_pct": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
@@ -66,7 +72,7 @@ summ = {
     "sm_ghz_under_ncu": num("sm__cycles_elapsed.avg.per_second"),
     "top_stalls_per_issue": dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:5]),
 }
-json.dump(summ, open(os.path.join(ROOT, "profiles", "ncu_summary.json"), "w"), indent=1)
+json.dump(summ, open(summary_path, "w"), indent=1)
 with open(os.path.join(ROOT, "profiles", f"{tag}_opcode_mix.txt"), "w") as f:
     f.write(f"{d['Kernel Name'][1]}, {steps} geodesic steps (ncu source page of {os.path.basename(rep)})\n")
     f.write(f"executed warp instructions {tot} = {tot / (steps / 32):.1f} per warp-step; FP64-pipe {fp / (steps / 32):.1f} per warp-step; "

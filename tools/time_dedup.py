@@ -19,6 +19,7 @@ ap.add_argument("--height", type=int, default=2160)
 ap.add_argument("--width", type=int, default=3840)
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
+os.environ["SCHW_DEDUP_REUSE"] = "0"          # every timed frame plans and integrates again
 hd = schw_b200.Handle(0)
 tex = np.random.default_rng(0).integers(0, 256, size=(a.height, a.width, 3), dtype=np.uint8)
 sc = schw_b200.make_scene(height=a.height, width=a.width)
