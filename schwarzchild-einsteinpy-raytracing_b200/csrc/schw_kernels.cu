@@ -519,8 +519,11 @@ persistent_tiles(const __grid_constant__ Job job, const __grid_constant__ StepPa
 // per ray and group, 8 coalesced STG.128 per thread every 4 steps, streaming).  Lanes whose ray has ended sit on the
 // fixed point of the flows (park) until the warp's last ray ends; the planar fast path is used when the rays allow it.
 // ---------------------------------------------------------------------------------------------
+#ifndef SCHW_FULL_MINBLOCKS
+#define SCHW_FULL_MINBLOCKS SCHW_MINBLOCKS
+#endif
 template <bool kPlanar>
-__global__ void __launch_bounds__(kBlock, kPlanar ? SCHW_MINBLOCKS : SCHW_MINBLOCKS_GENERAL)
+__global__ void __launch_bounds__(kBlock, kPlanar ? SCHW_FULL_MINBLOCKS : SCHW_MINBLOCKS_GENERAL)
 integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__ p0s, long long n,
                       const __grid_constant__ StepParams P, double *__restrict__ out_traj,
                       long long *__restrict__ out_rows, Counters *ctr, const int *__restrict__ select, int want)
@@ -625,9 +628,9 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
             const bool maybe = maybe_finished(S.q1r, P);
             tok = __all_sync(kFull, next & !maybe);
             quiet = tok ? true : (bool)__all_sync(kFull, !maybe);
-        } else {
-            step_BCB<true>(S, P, M);
-            flow_A<true>(S, P.delta, P.d_rs, P.rs, M);
+        } else {                                           // tilted rays: the trig memo would never hit
+            step_BCB<false>(S, P, M);
+            flow_A<false>(S, P.delta, P.d_rs, P.rs, M);
             quiet = __all_sync(kFull, !maybe_finished(S.q1r, P));
         }
         ++it;
@@ -1515,7 +1518,9 @@ static int launch_tiles_variant(schw_handle *h, const Job &job, long long qlen, 
         if (occ < 1) return fail(SCHW_E_CUDA, "kernel does not fit on an SM");
     }
     const long long want_blocks = (qlen + (long long)kBlock * R - 1) / ((long long)kBlock * R);
-    long long grid = (long long)h->sm_count * occ;
+    int use = occ;
+    if (const char *e = getenv("SCHW_TILE_CTAS")) { const int c = atoi(e); if (c >= 1 && c < occ) use = c; }   // (A/B measurements)
+    long long grid = (long long)h->sm_count * use;
     if (grid > want_blocks) grid = want_blocks;
     kern<<<(unsigned)grid, kBlock, 0, st>>>(job, P, h->ctr);
     h->launches += 1;
@@ -1558,9 +1563,11 @@ static int integrate_batch_impl(schw_handle *h, const double *d_q0s, const doubl
         if (coherent && tile_mode_for(h, n) == 2) rc = launch_tiles(h, job, (long long)n, P, st, false);
         else rc = launch_persistent(h, job, P, h->occ_batch, st, false);
         if (rc) return rc;
+        // not planar: the angle of a tilted ray changes every step, the trig memo never hits and its compare + vote per flow
+        // only cost issue slots (4e5 random rays: 44.6 -> 38.8 ms without it)
         job.want = 0;
         P.pl_enable = 0;
-        rc = launch_persistent(h, job, P, h->occ_batch, st, false);
+        rc = launch_variant<BatchJob, false, false>(h, job, P, h->occ_batch[0], st);
     } else {
         rc = launch_persistent(h, job, P, h->occ_batch, st);
     }
@@ -1916,7 +1923,8 @@ extern "C" int schw_render_dev_pitched(schw_handle *h, const schw_scene *scene, 
     if (n > 0 && (!d_rgb || !d_cls)) return fail(SCHW_E_INVALID, "null output");
     // Camera rays start at theta_obs with p_theta = -0.0: they are eligible for the planar fast path iff theta_obs is
     // the double nearest pi/2 (observer in the equatorial plane, the reference's only camera: raytracing.py:60-72).
-    if (sc.th_obs != 1.5707963267948966) P.pl_enable = 0;
+    const bool off_plane = sc.th_obs != 1.5707963267948966;
+    if (off_plane) P.pl_enable = 0;
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
     RenderJob job;
     job.sc = sc; job.tex = d_tex; job.rgb = d_rgb; job.cls = d_cls;
@@ -1940,7 +1948,10 @@ extern "C" int schw_render_dev_pitched(schw_handle *h, const schw_scene *scene, 
     begin_timed(h, st);
     // equatorial observer (every ray planar) + whole tiles: the tile kernel; otherwise the per-lane-refill kernel
     if (job.tile_mode == 2 && P.pl_enable && trig_memo_enabled()) rc = launch_tiles(h, job, job.qlen, P, st);
-    else rc = launch_persistent(h, job, P, h->occ_render, st);
+    else if (off_plane) {                       // tilted camera rays: no fast path, and the trig memo would never hit
+        CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
+        rc = n > 0 ? launch_variant<RenderJob, false, false>(h, job, P, h->occ_render[0], st) : SCHW_OK;
+    } else rc = launch_persistent(h, job, P, h->occ_render, st);
     end_timed(h, st);
     return rc;
 }
