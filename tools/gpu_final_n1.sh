@@ -18,9 +18,9 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 python tools/profile_render.py --height 2160 --width 3840 --reps 2 --batch 400000 > gpurun_out/plain_$TAG.log 2>&1 && tail -4 gpurun_out/plain_$TAG.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:persistent_tiles -c 1 -f -o gpurun_out/prof_render_4k_$TAG \
     python tools/profile_render.py --height 2160 --width 3840 --reps 1 > gpurun_out/ncu_render_$TAG.log 2>&1; echo "ncu render rc=$?"
-# general (tilted) rays through integrate_batch: the per-lane-refill kernel without the fast path (the probe kernel and the
-# skipped fast-path launch come first: -k selects the plain variant by its template arguments)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"persistent_rays<.*BatchJob, *1, *0>|persistent_rays<.*BatchJob, *true, *false>" -c 1 -f -o gpurun_out/prof_batch_general_$TAG \
+# general (tilted) rays through integrate_batch: launches = probe, fast-path kernel (exits at once: the probe says "not planar"),
+# the per-lane-refill kernel without fast path and trig memo -- the second persistent_rays launch
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:persistent_rays -s 1 -c 1 -f -o gpurun_out/prof_batch_general_$TAG \
     python tools/profile_render.py --height 64 --width 64 --reps 1 --batch 400000 > gpurun_out/ncu_batch_$TAG.log 2>&1; echo "ncu batch rc=$?"
 for kind in camera general; do
   timeout 300 python tools/bench_full.py --kind $kind --steps 2048 --out gpurun_out/full_${kind}_$TAG.json 2>&1 | tail -1 | cut -c1-330
