@@ -254,9 +254,11 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
-    def step_device():
+    def step_device(mid=None):
         hd.render_dev_pitched(scene, d_tex.data_ptr(), rb, re, rs, d_out.data_ptr(), 4 * w, d_out.data_ptr() + 3 * w, 4 * w,
                               stream=stream)
+        if mid is not None:
+            mid.record()
         if world > 1:
             dist.all_gather_into_tensor(d_all, d_out)
 
@@ -279,16 +281,19 @@ def main():
     if sampler:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev_mid = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]      # between this rank's kernel and the collective
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         flush.zero_()                                   # L2 flush, outside the per-step events
         ev[k][0].record()
-        step_device()
+        step_device(ev_mid[k])
         ev[k][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    own_kernel_ms = sum(a.elapsed_time(m) for (a, _), m in zip(ev, ev_mid)) / args.steps
+    wait_ms = sum(m.elapsed_time(b) for (_, b), m in zip(ev, ev_mid)) / args.steps
     kern_ms, _ = hd.last_kernel_ms()
     hd.last_status()
 
@@ -379,6 +384,10 @@ def main():
     else:
         steps_per_frame = float(steps_per_frame_local)
 
+    per_rank = None
+    if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, (round(own_kernel_ms, 3), round(wait_ms, 3)))
     if rank == 0:
         value = steps_per_frame * args.steps / (dev_ms * 1e-3)
         e2e_value = steps_per_frame * args.steps / e2e_s
@@ -432,6 +441,10 @@ def main():
             "roofline": roof,
             "clocks": clocks,
         }
+        if per_rank is not None:
+            # where a multi-rank frame goes: every rank's own kernel, then the collective (which includes waiting for the
+            # slowest rank)
+            line["per_rank"] = {"kernel_ms": [p[0] for p in per_rank], "all_gather_incl_wait_ms": [p[1] for p in per_rank]}
         if gather_check is not None:
             line["gather_check"] = gather_check
         if dedup is not None:

@@ -645,6 +645,142 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
     if (threadIdx.x == 0 && s_total) atomicAdd(&ctr->total_steps, s_total);
 }
 
+// The same kernel for planar rays with R rays per thread (R = 2: the loop control, the votes and the constant loads of a
+// loop body are shared by two geodesics, and at 4 CTAs/SM the compiler has the registers to keep staging pointers, store
+// addresses and constants resident instead of re-materialising them every step).  A warp owns R groups of 32 consecutive
+// rays; lane l carries ray l of each group.  Rows are staged and flushed exactly as above, group by group.
+template <int R>
+__global__ void __launch_bounds__(kBlock, R == 1 ? SCHW_MINBLOCKS : SCHW_TILE_MINBLOCKS)
+integrate_full_planar_kernel(const double *__restrict__ q0s, const double *__restrict__ p0s, long long n,
+                             const __grid_constant__ StepParams P, double *__restrict__ out_traj,
+                             long long *__restrict__ out_rows, Counters *ctr, const int *__restrict__ select, int want)
+{
+    if (select && *select != want) return;                 // (grid-uniform) see batch_probe_kernel
+    constexpr int kWarps = kBlock / 32;
+    // staging: 8 double2 (4 rows x 32 B) per ray, 16-byte pieces XOR-swizzled with the ray's lane so that both the
+    // lane-strided staging stores and the ray-contiguous flush loads are bank-conflict free (the padded layout of the
+    // one-ray kernel would exceed the 48 KB of static shared memory here)
+    __shared__ double2 s_stage[R][kWarps][32 * 8];
+    __shared__ int s_rows[R][kBlock];                      // rows stored by each ray (INT_MAX while it runs)
+    __shared__ unsigned long long s_total;
+    __shared__ Memo2 s_memo[R * kBlock];
+    if (threadIdx.x == 0) s_total = 0ull;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int l3 = (int)(lane >> 3), piece = (int)(lane & 7);
+    const size_t dstride = (size_t)4 * (size_t)P.steps * 2;       // double2 units between the rays of store j and store j+1
+    const int sw = (int)(lane & 7);
+    // in store j (0..7) this lane writes piece `piece` of ray L = 4 j + l3, staged at L*8 + (piece ^ (L & 7)), (L & 7) = 4 (j & 1) + l3
+    const int sidx0 = l3 * 8 + (piece ^ l3), sidx1 = (4 + l3) * 8 + (piece ^ (4 + l3));
+    RayState S[R];
+    bool active[R];
+    int pp_hi[R];
+    double2 *mine[R];
+    double2 *dst0[R];
+    const double2 *src0[R];
+    bool all_running = true, any_active = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const long long i = ((long long)blockIdx.x * R + r) * kBlock + threadIdx.x;
+        s_memo[r * kBlock + threadIdx.x].init(P.delta, P.h);
+        active[r] = i < n && P.steps > 0;
+        if (active[r]) {
+            const double2 *q = reinterpret_cast<const double2 *>(q0s + 4 * i), *p = reinterpret_cast<const double2 *>(p0s + 4 * i);
+            const double2 qa = __ldg(q), qb = __ldg(q + 1), pa = __ldg(p), pb = __ldg(p + 1);
+            const double q0[4] = {qa.x, qa.y, qb.x, qb.y}, p0[4] = {pa.x, pa.y, pb.x, pb.y};
+            init_state(S[r], q0, p0);
+        } else {
+            park(S[r], P);
+        }
+        s_rows[r][threadIdx.x] = active[r] ? 0x7fffffff : 0;
+        pp_hi[r] = active[r] ? P.pl_pp_hi : 0;
+        mine[r] = s_stage[r][warp] + lane * 8;
+        src0[r] = s_stage[r][warp];
+        dst0[r] = reinterpret_cast<double2 *>(out_traj + (size_t)(i - lane + l3) * (size_t)P.steps * 4) + piece;
+        all_running = all_running && __all_sync(kFull, active[r]);
+        any_active = any_active || __any_sync(kFull, active[r]);
+    }
+    int tok = 0, n_general = 0, it = 0;
+    bool quiet = false;                                    // (warp-uniform) no ray can end at the row about to be stored
+    bool first = true;
+    for (int step = 0; any_active; ++step) {               // (warp-uniform trip count)
+        const int slot = step & 3;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {                      // row `step`: q1 before the test
+            mine[r][(2 * slot) ^ sw] = make_double2(S[r].q1t, S[r].q1r);
+            mine[r][(2 * slot + 1) ^ sw] = make_double2(S[r].q1h, S[r].q1p);
+        }
+        if (!quiet || step == P.steps - 1) {
+            unsigned am_all = kFull, am_any = 0u;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (active[r]) {
+                    if (terminated(S[r].q1r, P) || step == P.steps - 1) {
+                        active[r] = false; pp_hi[r] = 0;
+                        s_rows[r][threadIdx.x] = step + 1;
+                        atomicAdd(&s_total, (unsigned long long)step);
+                        park(S[r], P);
+                    } else if (!(S[r].q1r == S[r].q1r)) {
+                        // a NaN r never terminates in the reference: every later row is NaN
+                        const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+                        S[r].q1t = S[r].q1h = S[r].q1p = S[r].q2t = S[r].q2r = S[r].q2h = S[r].q2p = nanv;
+                    }
+                }
+                const unsigned am = __ballot_sync(kFull, active[r]);
+                am_all &= am; am_any |= am;
+            }
+            any_active = am_any != 0u;
+            all_running = all_running && am_all == kFull;
+        }
+        if (slot == 3 || !any_active) {                    // flush rows [step - slot, step] of the warp's 32 R rays
+            __syncwarp();
+            const int base = step - slot;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                double2 *dst = dst0[r] + (size_t)base * 2;
+                if (all_running && slot == 3) {            // all four rows of all rays are valid: eight full-line stores per group
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) __stcs(dst + j * dstride, src0[r][32 * j + ((j & 1) ? sidx1 - 32 : sidx0)]);
+                } else {
+                    const int *rows_w = s_rows[r] + (threadIdx.x & ~31);
+#pragma unroll 1
+                    for (int j = 0; j < 8; ++j) {
+                        const int L = 4 * j + l3;
+                        if ((piece >> 1) <= slot && base + (piece >> 1) < rows_w[L])
+                            __stcs(dst + j * dstride, src0[r][L * 8 + (piece ^ (L & 7))]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (!any_active) break;
+        if (first) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) flow_A<false>(S[r], P.h, P.h_rs, P.rs, s_memo[r * kBlock + threadIdx.x]);
+            first = false;
+        }
+        bool next = false;
+        step_BCBA_planar_n<R>(S, P, &s_memo[threadIdx.x], kBlock, pp_hi, tok, next, n_general);
+        bool maybe = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) maybe |= maybe_finished(S[r].q1r, P);
+        tok = __all_sync(kFull, next & !maybe);
+        quiet = tok ? true : (bool)__all_sync(kFull, !maybe);
+        ++it;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const long long i = ((long long)blockIdx.x * R + r) * kBlock + threadIdx.x;
+        if (i < n && out_rows) out_rows[i] = s_rows[r][threadIdx.x];
+    }
+    if (lane == 0 && it) {
+        atomicAdd(&ctr->warp_iters, (unsigned long long)it * R);
+        atomicAdd(&ctr->planar_iters, (unsigned long long)(it - n_general) * R);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_total) atomicAdd(&ctr->total_steps, s_total);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Decimated trajectories: the same integration as integrate_full_kernel, but only the rows
 // whose step index appears in the ascending list row_idx[0..nidx) are written, to out (n, nidx, 4).  This is what
@@ -1614,12 +1750,16 @@ static int integrate_full_impl(schw_handle *h, const double *d_q0s, const double
 {
     StepParams P = P0;
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    const unsigned grid2 = (unsigned)((n + 2 * kBlock - 1) / (2 * kBlock));
+    const char *fr = getenv("SCHW_FULL_RAYS");              // 1: one ray per thread on planar batches too (A/B measurements)
+    const bool two = !(fr && fr[0] == '1');
     CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
     begin_timed(h, st);
     if (P.pl_enable && trig_memo_enabled() && !planar_forced()) {
         // the device chooses between the kernel with the planar fast path and the plain one (batch_probe_kernel)
         batch_probe_kernel<<<1, 256, 0, st>>>(d_q0s, d_p0s, (long long)n, &h->ctr->batch_planar);
-        integrate_full_kernel<true><<<grid, kBlock, 0, st>>>(d_q0s, d_p0s, (long long)n, P, d_traj, d_rows, h->ctr, &h->ctr->batch_planar, 1);
+        if (two) integrate_full_planar_kernel<2><<<grid2, kBlock, 0, st>>>(d_q0s, d_p0s, (long long)n, P, d_traj, d_rows, h->ctr, &h->ctr->batch_planar, 1);
+        else integrate_full_kernel<true><<<grid, kBlock, 0, st>>>(d_q0s, d_p0s, (long long)n, P, d_traj, d_rows, h->ctr, &h->ctr->batch_planar, 1);
         P.pl_enable = 0;
         integrate_full_kernel<false><<<grid, kBlock, 0, st>>>(d_q0s, d_p0s, (long long)n, P, d_traj, d_rows, h->ctr, &h->ctr->batch_planar, 0);
         h->launches += 3;

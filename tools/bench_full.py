@@ -21,8 +21,8 @@ import schw_b200  # noqa: E402
 import torch  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--rays", type=int, default=227328, help="default: two full waves of 148 SMs x 6 CTAs x 128 threads")
-ap.add_argument("--steps", type=int, default=512)
+ap.add_argument("--rays", type=int, default=454656, help="default: whole waves of both kernels (148 SMs x 6 CTAs x 128 threads x 4 = 148 x 4 x 256 x 3)")
+ap.add_argument("--steps", type=int, default=1024)
 ap.add_argument("--delta", type=float, default=0.01)
 ap.add_argument("--kind", default="camera", choices=["camera", "general"])
 ap.add_argument("--reps", type=int, default=3)
