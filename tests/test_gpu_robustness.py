@@ -144,3 +144,30 @@ def test_thresholds_a_few_ulps_apart(handle, orc):
         assert np.array_equal(ns, ns_ref), steps
         assert np.allclose(out, ref, rtol=1e-12, atol=1e-12, equal_nan=True), steps
     assert set(np.unique(ns)) >= {0, 400}
+
+
+def test_trajectory_kernels_agree_bit_for_bit_on_camera_rays(handle, monkeypatch):
+    """integrate_batch_full on planar (camera) rays: the two-rays-per-thread kernel (shipped), the one-ray kernel with the
+    fast path and the general kernel (SCHW_PLANAR=0) must store the same rows, bit for bit -- ragged batch (not a multiple
+    of 2 x 128 rays), rays ending at every position of a 4-row group, step cap hit by some."""
+    import schw_b200
+    sc = schw_b200.make_scene(height=19, width=37, delta=0.05)
+    q0s, ic = handle.initial_conditions(sc)
+    p0s = ic[:, :4].copy()
+    steps = 1101
+    outs = []
+    for env in (dict(), dict(SCHW_FULL_RAYS="1"), dict(SCHW_PLANAR="0")):
+        for k in ("SCHW_FULL_RAYS", "SCHW_PLANAR"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        traj, rows = handle.integrate_batch_full(q0s, p0s, steps, 0.05, 2.0, 31.0, 1.0, want_rows=True)
+        outs.append((traj, rows, handle.last_counters()))
+    for traj, rows, ctr in outs[1:]:
+        assert np.array_equal(rows, outs[0][1]) and np.array_equal(traj, outs[0][0], equal_nan=True)
+    rows = outs[0][1]
+    assert rows.min() < steps and rows.max() == steps and len(set(int(r) % 4 for r in rows)) == 4
+    assert outs[0][2][2] > 0.9 * outs[0][2][1] and outs[2][2][2] == 0          # fast path taken / not taken
+    fin = handle.integrate_batch(q0s, p0s, steps, 0.05, 2.0, 31.0, 1.0)
+    ended = rows < steps
+    assert np.array_equal(fin[ended], outs[0][0][ended, rows[ended] - 1])

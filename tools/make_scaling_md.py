@@ -49,6 +49,11 @@ if os.path.exists(sw):
         shutil.copy(sw, os.path.join(ROOT, "profiles", f"{tag}_sweep_n8.json"))
         s = json.loads(lines[-1])
         out += ["", f"Config 5 (`tools/bench_sweep.py` under torchrun on 8 GPUs, `{tag}_sweep_n8.json`): " + json.dumps({k: s[k] for k in s if k in ("frames", "height", "width", "delta", "seconds", "frames_per_s", "steps_per_s", "wall_s")})]
+bd = os.path.join(ROOT, "profiles", f"{tag}_n8_breakdown.json")
+if os.path.exists(bd):
+    b = json.loads([l for l in open(bd) if l.startswith("{")][-1])
+    out += ["", f"Where an 8-rank frame goes (`{tag}_n8_breakdown.json`: `bench.py --gpus 8 --steps 5`, frame {b['frame_ms']:.2f} ms): own kernel per rank "
+            f"{b['per_rank']['kernel_ms']} ms, then all_gather incl. waiting for the slowest rank {b['per_rank']['all_gather_incl_wait_ms']} ms."]
 mr = os.path.join(ROOT, "gpurun_out", f"pytest_multirank_{tag}.log")
 if os.path.exists(mr):
     shutil.copy(mr, os.path.join(ROOT, "profiles", f"{tag}_pytest_multirank.log"))
