@@ -28,6 +28,14 @@ def test_bench_line_small_frame():
     assert d["e2e"]["h2d_bytes_per_step"] == 270 * 480 * 3 and d["e2e"]["d2h_bytes_per_step"] == 270 * 480 * 4
     r = d["roofline"]
     assert r["bound"] == "fp64" and r["unit"] == "TFLOP/s" and 20 < r["peak"] < 45 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    # frac is a utilisation of the FP64 pipe computed in the run (loop bodies x FP64 instructions per body from the SASS of
+    # this build), never above 1; the algorithmic figure lives in its own fields
+    assert 0.3 < r["frac"] <= 1.0 and r["fp64_instr_per_loop_body"]["fast_path"] == 100 and r["algorithmic_flop_per_step"] == 312
+    assert r["algorithmic_tflops"] > r["achieved"] * 0.9 and 0.9 < r["lane_utilisation"] <= 1.0
+    assert "gather_check" not in d                                  # single GPU: nothing gathered
+    oc = d["other_configs"]
+    assert oc["config1_400x400"]["steps"] > 8e8 and oc["config3_1920x1080"]["frame_ms"] > oc["config1_400x400"]["frame_ms"]
+    assert len(d["entry_point"]) == 2 and d["entry_point"][0]["nonblack_pixels"] > 100000
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 1e5 and "rows" in c["sample"]
     assert "workload" in d["config"] and "model" not in d["config"]
