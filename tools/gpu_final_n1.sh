@@ -27,7 +27,7 @@ for kind in camera general; do
 done
 SCHW_FULL_RAYS=1 timeout 300 python tools/bench_full.py --kind camera --out gpurun_out/full_camera_one_ray_per_thread_$TAG.json 2>&1 | tail -1 | cut -c1-330
 timeout 300 python tools/bench_full.py --kind camera --rays 4096 --steps 8192 --out gpurun_out/full_camera_4096x8192_$TAG.json 2>&1 | tail -1 | cut -c1-330
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:integrate_full_kernel -c 1 -f -o gpurun_out/prof_full_$TAG \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:integrate_full_planar_kernel -c 1 -f -o gpurun_out/prof_full_$TAG \
     python tools/bench_full.py --kind camera --reps 1 > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 timeout 300 python tools/step_probe.py --out gpurun_out/step_probe_$TAG.json > /dev/null 2>&1; echo "probe rc=$?"
 timeout 600 python tools/ab_tile.py --out gpurun_out/ab_tile_$TAG.json > /dev/null 2>&1; echo "ab_tile rc=$?"
