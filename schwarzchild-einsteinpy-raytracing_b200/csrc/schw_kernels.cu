@@ -1,19 +1,23 @@
 // schw_kernels.cu — sm_100a kernels and the C ABI (include/schw_b200.h) of libschw_b200.so.
 //
 // Kernel inventory:
-//   persistent_rays<RenderJob>  camera IC -> FANTASY stepper -> terminate -> classify -> texel  (the hot path)
-//   persistent_rays<BatchJob>   integrate_batch on caller-supplied (q0,p0)
-//   integrate_full_kernel       integrate_batch_full (per-step trajectory store)
-//   ic_kernel / classify_kernel stages 1+2 and 5 alone (boundary + parity testing)
-//   flat_kernel                 flat-space comparison render
-//   dfma_probe_kernel           FP64 FMA peak measurement
+//   persistent_tiles<RenderJob,R>   camera IC -> FANTASY stepper -> terminate -> classify -> texel: THE hot path (whole
+//                                   32-pixel tiles per warp, R = 2 rays per thread on large launches)
+//   persistent_tiles<BatchJob,R>    the distinct rays of a de-duplicated frame (coherent: sorted by camera angle)
+//   persistent_rays<Job,memo,planar>  per-lane refill: integrate_batch on caller-supplied (q0,p0); render with an
+//                                   observer off the equatorial plane; A/B switch SCHW_TILE_MODE
+//   integrate_full_planar_kernel<2>, integrate_full_kernel<planar>, integrate_rows_kernel
+//                                   integrate_batch_full (per-step trajectory store, full 128-byte lines) and its decimated form
+//   dedup_{key,heads,scatter,epilogue}_kernel   geodesic de-duplication (sort/scan by cub)
+//   ic_kernel / ic_px_kernel / classify_kernel  stages 1+2 and 5 alone (boundary + parity testing)
+//   flat_kernel / flat_dirs_kernel / flat_traj_kernel   flat-space comparison render
+//   dfma_probe_kernel, step_probe_kernel<R,CTAs>, math_probe_kernel   measurement and accuracy probes
 //
-// Scheduling: FP64-pipe bound, no reuse, ~4 B of output per ~1.5 M flops => no shared-memory
-// tiling or TMA staging is useful.  What matters is keeping all 64 FP64 lanes of every SM busy
-// although rays need 3 k .. 200 k steps: the kernels are persistent (grid = SMs x resident CTAs)
-// and every *lane* pulls its next ray from a global queue the moment its ray terminates
-// (warp-ballot compaction of the set of lanes that need work + one aggregated atomic per warp),
-// so a warp never idles lanes while rays remain.
+// Scheduling: FP64-pipe bound, no reuse, ~4 B of output per ~1.5 M flops => no shared-memory tiling or TMA staging is
+// useful.  What matters is keeping all 64 FP64 lanes of every SM busy although rays need 3 k .. 200 k steps: the kernels
+// are persistent (grid = SMs x resident CTAs) over a global queue of 32-pixel tiles in longest-first order; a warp takes
+// whole tiles (neighbouring pixels need almost the same number of steps) or, for incoherent batches, every lane refills
+// itself the moment its ray ends (warp-ballot compaction + one aggregated atomic per warp).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +27,7 @@
 #include <vector>
 #include <algorithm>
 #include <utility>
+#include <type_traits>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -519,11 +524,8 @@ persistent_tiles(const __grid_constant__ Job job, const __grid_constant__ StepPa
 // per ray and group, 8 coalesced STG.128 per thread every 4 steps, streaming).  Lanes whose ray has ended sit on the
 // fixed point of the flows (park) until the warp's last ray ends; the planar fast path is used when the rays allow it.
 // ---------------------------------------------------------------------------------------------
-#ifndef SCHW_FULL_MINBLOCKS
-#define SCHW_FULL_MINBLOCKS SCHW_MINBLOCKS
-#endif
 template <bool kPlanar>
-__global__ void __launch_bounds__(kBlock, kPlanar ? SCHW_FULL_MINBLOCKS : SCHW_MINBLOCKS_GENERAL)
+__global__ void __launch_bounds__(kBlock, kPlanar ? SCHW_MINBLOCKS : SCHW_MINBLOCKS_GENERAL)
 integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__ p0s, long long n,
                       const __grid_constant__ StepParams P, double *__restrict__ out_traj,
                       long long *__restrict__ out_rows, Counters *ctr, const int *__restrict__ select, int want)
@@ -569,16 +571,10 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
     bool any_active = __any_sync(kFull, active);           // (warp-uniform)
     bool quiet = false;                                    // (warp-uniform) no ray can end at the row about to be stored
     bool first = true;
-#ifndef SCHW_FULL_UNROLL
-#define SCHW_FULL_UNROLL 1
-#endif
-    // (SCHW_FULL_UNROLL=4 unrolls the four steps of a row group so that the staging offsets and the flush test are
-    //  compile-time constants: measured equal, 0.567 vs 0.562 of the HBM figure, so the rolled loop is kept)
-    for (int base4 = 0; any_active; base4 += SCHW_FULL_UNROLL) {               // (warp-uniform trip count)
-#pragma unroll
-      for (int sub = 0; sub < SCHW_FULL_UNROLL; ++sub) {
-        const int step = base4 + sub;
-        const int slot = SCHW_FULL_UNROLL == 4 ? sub : (step & 3);
+    // (unrolling the four steps of a row group, so that staging offsets and the flush test become compile-time constants,
+    //  measured equal: 0.567 vs 0.562 of the HBM figure -- the rolled loop is kept)
+    for (int step = 0; any_active; ++step) {               // (warp-uniform trip count)
+        const int slot = step & 3;
         // row `step`: q1 before the test (parked lanes stage their fixed point: never flushed)
         mine[2 * slot] = make_double2(S.q1t, S.q1r);
         mine[2 * slot + 1] = make_double2(S.q1h, S.q1p);
@@ -634,7 +630,6 @@ integrate_full_kernel(const double *__restrict__ q0s, const double *__restrict__
             quiet = __all_sync(kFull, !maybe_finished(S.q1r, P));
         }
         ++it;
-      }
     }
     if (i < n && out_rows) out_rows[i] = s_rows[threadIdx.x];
     if (lane == 0 && it) {
@@ -1224,7 +1219,7 @@ struct schw_handle {
     int launches = 0;
     Counters *ctr = nullptr;
     int occ_render[3] = {0, 0, 0}, occ_batch[3] = {0, 0, 0};   // filled on first use, see launch_persistent
-    int occ_tiles[3] = {0, 0, 0};                               // persistent_tiles<R>, index R
+    int occ_tiles[2][3] = {{0, 0, 0}, {0, 0, 0}};               // persistent_tiles<RenderJob | BatchJob, R>, index [job][R]
     // grow-only scratch
     DevBuf in_a, in_b, in_c, tex, rgb, cls, fq, ic, hit, texel, nsteps, traj, rows, order;
     DevBuf dd_keys, dd_keys2, dd_pix, dd_pix2, dd_head, dd_uid, dd_map, dd_tmp, dd_q0, dd_p0, dd_fq, dd_ns;   // de-duplication
@@ -1648,7 +1643,7 @@ template <class Job, int R>
 static int launch_tiles_variant(schw_handle *h, const Job &job, long long qlen, const StepParams &P, cudaStream_t st)
 {
     auto kern = persistent_tiles<Job, R>;
-    int &occ = h->occ_tiles[R];                   // (RenderJob and BatchJob instances use the same registers and shared memory)
+    int &occ = h->occ_tiles[std::is_same<Job, RenderJob>::value ? 0 : 1][R];
     if (occ == 0) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, 0));
         if (occ < 1) return fail(SCHW_E_CUDA, "kernel does not fit on an SM");

@@ -99,6 +99,7 @@ def test_step_loop_sass_budget():
     for k in d["kernels"]:                       # the shipped tile kernel (2 rays per thread), its 1-ray form, the per-lane-refill kernel
         assert k["bra_div_in_kernel"] == 0, k["kernel"]
         assert 90 <= k["fp64_per_body_fast_path"] <= 100 and k["fp64_per_body_general"] <= 121, k["kernel"]
+    assert d["schw_kernels"] >= 20 and d["bra_div_all_schw_kernels"] == 0      # every kernel of the library, not only the render ones
     sys.path.insert(0, ROOT)
     import bench
     assert d["csrc_sha"] == bench.csrc_sha()

@@ -110,9 +110,20 @@ def main():
         cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
         txt = subprocess.run(["nvdisasm", "-gi", "-c", cubin], cwd=d, capture_output=True, text=True).stdout
     per_kernel = [analyse(txt, ksrc, dsrc, *k) for k in KERNELS]
+    # BRA.DIV in every kernel of namespace schw (cub's sort/scan kernels have their own and are not ours)
+    bra_div_all, cur = collections.Counter(), None
+    for line in txt.splitlines():
+        m = re.match(r"\s*\.section\s+\.text\.(\S+?),", line)
+        if m:
+            cur = m.group(1) if m.group(1).startswith("_ZN4schw") else None
+            if cur:
+                bra_div_all[cur] += 0
+        elif cur and "BRA.DIV" in line:
+            bra_div_all[cur] += 1
     out = dict(per_kernel[0])                 # the shipped render kernel at the top level (what bench.py reads)
     out.update({
         "csrc_sha": csrc_sha(), "kernels": per_kernel,
+        "bra_div_all_schw_kernels": sum(bra_div_all.values()), "schw_kernels": len(bra_div_all),
         "how": "nvdisasm -gi of the built library: instructions whose inline chain passes through the kernel's call of the step "
                "function (step_BCBA_planar / step_BCBA_planar_n<R>), split by call site (tools/loop_body_fp64.py), per ray-step.  "
                "'general' = all three flows and the mixing off the fast path with the trig memo hitting; the memo-miss "
