@@ -1628,14 +1628,15 @@ static int launch_persistent(schw_handle *h, const Job &job, const StepParams &P
 }
 
 // The whole-tile kernel (persistent_tiles<Job, R>), R rays per thread.  Two rays per thread (4 CTAs/SM) are faster once a
-// warp gets many tiles -- 4K frame 297.8 -> 292.4 ms, 1080p 75.5 -> 74.3 ms -- while one ray per thread (6 CTAs/SM: smaller
-// units of work) ends a short launch sooner -- a 1/8 shard of the 4K frame 37.8 vs 38.0 ms, 400x400 6.85 vs 7.11 ms
-// (profiles/r02_ab_tile.json).  SCHW_TILE_RAYS=1|2 forces one (A/B measurements).
+// warp gets a few tiles -- 4K frame 297.9 -> 292.4 ms, 1080p 75.5 -> 74.3 ms, a 1/8 shard of the 4K frame 37.9 -> 37.7 ms,
+// a 1/16 shard 19.48 -> 19.39 ms -- while one ray per thread (6 CTAs/SM: smaller units of work) ends a short launch sooner:
+// 14 400 tiles 17.38 vs 17.52 ms, 400x400 (5200 tiles) 6.85 vs 7.1 ms (profiles/r02_ab_tile.json, tools/ab_tail.sh).
+// SCHW_TILE_RAYS=1|2 forces one (A/B measurements).
 static int tile_rays(long long qlen)
 {
     const char *e = getenv("SCHW_TILE_RAYS");
     if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
-    return qlen / 32 >= 40000 ? SCHW_TILE_RAYS : 1;
+    return qlen / 32 >= 16000 ? SCHW_TILE_RAYS : 1;
 }
 static int tile_mode_for(const schw_handle *, long long);
 
@@ -1966,7 +1967,6 @@ extern "C" int schw_classify(schw_handle *h, const schw_scene *scene, const doub
 // out the expensive tiles first leaves the cheap captured rays for the end of the launch, which halves the
 // end-of-frame tail (it matters when a frame is split over 8 GPUs: ~50 ms of work per GPU against a ~4 ms tail).
 // Purely a scheduling hint: every ray's result is independent of the order.
-static int tile_rays(long long qlen);
 static int build_tile_order(schw_handle *h, const schw_scene *s, const SceneParams &sc, cudaStream_t st,
                             const int32_t **d_order, int *tiles_per_row, long long *qlen)
 {
@@ -1976,13 +1976,8 @@ static int build_tile_order(schw_handle *h, const schw_scene *s, const ScenePara
     *qlen = ntiles * 32;
     *d_order = nullptr;
     if (ntiles == 0) return SCHW_OK;
-    // SCHW_TAIL_STRATIFY=c (experiment, default off): the last round of the queue (one tile per resident warp slot) is not the
-    // W shortest tiles but every c-th of the c*W shortest, so that its durations span a range and the warps -- which become
-    // free at different times -- can end together
-    const char *ts = getenv("SCHW_TAIL_STRATIFY");
-    const double strat = ts ? atof(ts) : 0.0;
     const double key[12] = {(double)sc.height, (double)sc.width, (double)sc.row_begin, (double)sc.row_stride, (double)sc.nrows,
-                            sc.plane_width, sc.plane_height, sc.obs[0], sc.obs[1], sc.obs[2], s->mass, 1.0 + strat};
+                            sc.plane_width, sc.plane_height, sc.obs[0], sc.obs[1], sc.obs[2], s->mass, 1.0};
     if (h->order_tiles == ntiles && memcmp(key, h->order_key, sizeof(key)) == 0) {
         *d_order = (const int32_t *)h->order.p;
         return SCHW_OK;
@@ -2018,19 +2013,9 @@ static int build_tile_order(schw_handle *h, const schw_scene *s, const ScenePara
     std::sort(tiles.begin(), tiles.end());
     std::vector<int32_t> order((size_t)ntiles);
     for (size_t t = 0; t < (size_t)ntiles; ++t) order[t] = tiles[t].second;
-    if (strat >= 1.0) {
-        const int R = tile_rays(ntiles * 32);
-        const long long W = (long long)h->sm_count * (R == 1 ? SCHW_MINBLOCKS : SCHW_TILE_MINBLOCKS) * (kBlock / 32) * R;
-        const long long m = (long long)(strat * (double)W);
-        if (W > 0 && m <= ntiles && W < m) {
-            std::vector<char> pick((size_t)m, 0);
-            for (long long k = 0; k < W; ++k) pick[(size_t)llround((double)k * (double)(m - 1) / (double)(W - 1))] = 1;
-            std::vector<int32_t> head, tail;
-            for (long long k = 0; k < m; ++k) (pick[(size_t)k] ? tail : head).push_back(order[(size_t)(ntiles - m + k)]);
-            std::copy(head.begin(), head.end(), order.begin() + (ntiles - m));
-            std::copy(tail.begin(), tail.end(), order.begin() + (ntiles - m) + (long long)head.size());
-        }
-    }
+    // (Measured and rejected, r02: a "stratified" last round -- every c-th of the c*W shortest tiles instead of the W shortest,
+    //  so that warps which become free at different times could end together -- helps one shard size by 0.5 ms and costs
+    //  0.2-0.5 ms at others: bin-packing noise, not a rule.)
     ENSURE(h->order, (size_t)ntiles * sizeof(int32_t));
     CU(cudaMemcpyAsync(h->order.p, order.data(), (size_t)ntiles * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));       // `order` is a local
