@@ -86,6 +86,44 @@ try:
             rel = np.abs(out[:, 1] - fq[:, 1]) / np.abs(fq[:, 1])
         esc = ours["cls"].reshape(-1) >= 2                # escaped rays (well-posed in the default scene)
         same_side = ((out[:, 1] >= sc.r_max) == (fq[:, 1] >= sc.r_max))
+        # who the disagreeing rays are: band G = |b / (3 sqrt(3) M) - 1| < 1e-3 with b = |p_phi / p_t|; band H = the
+        # trajectory reaches r < 2.5 M (the horizon blow-up band), measured on our own trajectory of each such ray
+        # (integrate_batch_full).  And what they do to the image: classes of the reference kernel's final states (our
+        # classify stage, raytracing.py:166-273) next to the frame's.
+        ic = ours["ic"]
+        b = np.abs(ic[:, 3]) / np.abs(ic[:, 0])
+        in_g = np.abs(b / (3.0 * np.sqrt(3.0) * sc.mass) - 1.0) < 1e-3
+        bad = ~same_side
+        kb = np.flatnonzero(bad)[:4096]
+        in_h = np.zeros(n, bool); rmin_bad = np.full(n, np.nan)
+        if kb.size:
+            cap = int(nsteps[kb].max()) + 1
+            traj, rows = hd.integrate_batch_full(q0s[kb], p0s[kb], cap, sc.delta, 2.0 * sc.mass, sc.r_max, 1.0, want_rows=True)
+            for m, k in enumerate(kb):
+                rmin_bad[k] = np.nanmin(traj[m, :max(int(rows[m]), 1), 1])
+            in_h[kb] = rmin_bad[kb] < 2.5 * sc.mass
+            del traj
+        # the rays neither band explains: how do BOTH kernels react to a 1-ulp change of their initial momentum?
+        left = kb[~(in_g[kb] | in_h[kb])]
+        ulp_probe = []
+        if left.size:
+            _, first = np.unique(p0s[left], axis=0, return_index=True)
+            for k in left[np.sort(first)][:4]:
+                E = np.repeat(p0s[k][None, :], 9, 0)
+                for m, (c, d_) in enumerate(((0, 1), (0, -1), (1, 1), (1, -1), (3, 1), (3, -1), (3, 2), (3, -2))):
+                    for _ in range(abs(d_)):
+                        E[m + 1, c] = np.nextafter(E[m + 1, c], np.inf * d_)
+                Qe = np.repeat(q0s[k][None, :], 9, 0)
+                mine_e = hd.integrate_batch(Qe, E, sc.steps, sc.delta, 2.0 * sc.mass, sc.r_max, 1.0)
+                ref_e, _ = integ.integrate_batch(Qe, E)
+                ulp_probe.append({"b_over_bcrit": float(b[k] / (3.0 * np.sqrt(3.0) * sc.mass)),
+                                  "pixels_with_this_ray": int((p0s[left] == p0s[k]).all(1).sum()),
+                                  "min_r_of_our_stored_rows": float(rmin_bad[k]),
+                                  "r_final_ours_over_1ulp_ensemble": [float(v) for v in mine_e[:, 1]],
+                                  "r_final_reference_over_1ulp_ensemble": [float(v) for v in ref_e[:, 1]]})
+        cls_ref = hd.classify(sc, out, ic[:, 4].copy(), ic[:, 5].copy(), None)["cls"]
+        cls_ours = ours["cls"].reshape(-1)
+        relq = np.abs(out - fq) / np.maximum(np.abs(fq), 1.0)
         run.update({
             "rays": n, "steps": steps,
             "reference_gpu": {"kernel_ms": kern_ms, "steps_per_s": steps / (kern_ms * 1e-3),
@@ -95,7 +133,23 @@ try:
             "speedup_kernel": kern_ms / ours_ms,
             "agreement": {"escaped_rays": int(esc.sum()),
                           "max_rel_err_r_final_escaped": float(np.nanmax(rel[esc])) if esc.any() else None,
-                          "escape_side_mismatches_all_rays": int((~same_side).sum())},
+                          "max_err_final_state_escaped_t_r_th_ph": [float(np.nanmax(relq[esc, k])) for k in range(4)] if esc.any() else None,
+                          "escape_side_mismatches_all_rays": int(bad.sum()),
+                          "of_those_in_band_g": int((bad & in_g).sum()),
+                          "of_those_examined": int(kb.size),
+                          "of_those_in_band_h_trajectory_reaches_r_below_2.5M": int((bad & ~in_g & in_h).sum()),
+                          "of_those_outside_both_bands": int(kb.size - (in_g[kb] | in_h[kb]).sum()),
+                          "b_over_bcrit_range_of_those": [float((b[kb] / (3.0 * np.sqrt(3.0) * sc.mass)).min()),
+                                                          float((b[kb] / (3.0 * np.sqrt(3.0) * sc.mass)).max())] if kb.size else None,
+                          "nan_rays_ours_and_reference": [int((~(fq[:, 1] == fq[:, 1])).sum()), int((~(out[:, 1] == out[:, 1])).sum())],
+                          "outside_both_bands_ulp_probe": ulp_probe,
+                          "outside_both_bands_sample": [
+                              {"b_over_bcrit": float(b[k] / (3.0 * np.sqrt(3.0) * sc.mass)), "r_final_ours": float(fq[k, 1]),
+                               "r_final_reference": float(out[k, 1]), "nsteps_ours": int(nsteps[k]), "class_ours": int(cls_ours[k]),
+                               "class_of_reference_state": int(cls_ref[k])}
+                              for k in kb[~(in_g[kb] | in_h[kb])][:8]],
+                          "class_mismatches_all_pixels": int((cls_ref != cls_ours).sum()),
+                          "class_mismatches_outside_band_g": int(((cls_ref != cls_ours) & ~in_g).sum())},
         })
         res["runs"].append(run)
         print(json.dumps(run), flush=True)
