@@ -1747,8 +1747,12 @@ static int integrate_full_impl(schw_handle *h, const double *d_q0s, const double
     StepParams P = P0;
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
     const unsigned grid2 = (unsigned)((n + 2 * kBlock - 1) / (2 * kBlock));
-    const char *fr = getenv("SCHW_FULL_RAYS");              // 1: one ray per thread on planar batches too (A/B measurements)
-    const bool two = !(fr && fr[0] == '1');
+    // Planar batches: two rays per thread once the batch fills the resident grid of that kernel (sm_count x 4 CTAs x 256
+    // rays = 151 552 on a B200: measured 5 % faster there, 10 % at 454 656 rays), one ray per thread below it, where twice
+    // the CTAs spread over more SMs (4096 rays x 8192 rows: 3.7 vs 4.8 ms).  SCHW_FULL_RAYS=1|2 forces one (A/B measurements).
+    const char *fr = getenv("SCHW_FULL_RAYS");
+    const bool two = (fr && (fr[0] == '1' || fr[0] == '2')) ? fr[0] == '2'
+                                                            : n >= (int64_t)h->sm_count * SCHW_TILE_MINBLOCKS * 2 * kBlock;
     CU(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), st));
     begin_timed(h, st);
     if (P.pl_enable && trig_memo_enabled() && !planar_forced()) {

@@ -147,8 +147,8 @@ def test_thresholds_a_few_ulps_apart(handle, orc):
 
 
 def test_trajectory_kernels_agree_bit_for_bit_on_camera_rays(handle, monkeypatch):
-    """integrate_batch_full on planar (camera) rays: the two-rays-per-thread kernel (shipped), the one-ray kernel with the
-    fast path and the general kernel (SCHW_PLANAR=0) must store the same rows, bit for bit -- ragged batch (not a multiple
+    """integrate_batch_full on planar (camera) rays: the two-rays-per-thread kernel (large batches), the one-ray kernel with the
+    fast path (small batches), the default choice and the general kernel (SCHW_PLANAR=0) must store the same rows, bit for bit -- ragged batch (not a multiple
     of 2 x 128 rays), rays ending at every position of a 4-row group, step cap hit by some."""
     import schw_b200
     sc = schw_b200.make_scene(height=19, width=37, delta=0.05)
@@ -156,7 +156,7 @@ def test_trajectory_kernels_agree_bit_for_bit_on_camera_rays(handle, monkeypatch
     p0s = ic[:, :4].copy()
     steps = 1101
     outs = []
-    for env in (dict(), dict(SCHW_FULL_RAYS="1"), dict(SCHW_PLANAR="0")):
+    for env in (dict(SCHW_FULL_RAYS="2"), dict(SCHW_FULL_RAYS="1"), dict(), dict(SCHW_PLANAR="0")):
         for k in ("SCHW_FULL_RAYS", "SCHW_PLANAR"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
@@ -168,7 +168,7 @@ def test_trajectory_kernels_agree_bit_for_bit_on_camera_rays(handle, monkeypatch
     rows = outs[0][1]
     assert rows.min() < steps and rows.max() == steps and len(set(int(r) % 4 for r in rows)) == 4
     # fast path taken (partly: at this coarse step the bound on |p_theta| is small and rays are handed to the general flow) / never
-    assert 0 < outs[0][2][2] <= outs[0][2][1] and outs[2][2][2] == 0
+    assert 0 < outs[0][2][2] <= outs[0][2][1] and outs[3][2][2] == 0
     fin = handle.integrate_batch(q0s, p0s, steps, 0.05, 2.0, 31.0, 1.0)
     ended = rows < steps
     assert np.array_equal(fin[ended], outs[0][0][ended, rows[ended] - 1])
