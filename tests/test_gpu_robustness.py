@@ -172,3 +172,28 @@ def test_trajectory_kernels_agree_bit_for_bit_on_camera_rays(handle, monkeypatch
     fin = handle.integrate_batch(q0s, p0s, steps, 0.05, 2.0, 31.0, 1.0)
     ended = rows < steps
     assert np.array_equal(fin[ended], outs[0][0][ended, rows[ended] - 1])
+
+
+def test_trajectory_kernel_choice_by_batch_size_changes_no_bit(handle, monkeypatch):
+    """integrate_batch_full picks the two-rays-per-thread kernel once a planar batch fills its resident grid (sm_count x 4 CTAs
+    x 256 rays) and the one-ray kernel below that; a batch just above the threshold must give the rows of the forced one-ray
+    kernel, bit for bit, and the device counters must show which kernel ran (warp iterations are counted per ray slot)."""
+    import schw_b200
+    n = handle.device_info()["sm_count"] * 4 * 256 + 77            # ragged, just above the threshold
+    sc = schw_b200.make_scene(height=64, width=96)
+    q0s, ic = handle.initial_conditions(sc)
+    pick = np.arange(n) % q0s.shape[0]
+    q0 = np.ascontiguousarray(q0s[pick]); p0 = np.ascontiguousarray(ic[pick, :4])
+    steps = 6
+    outs = {}
+    for mode in ("", "1", "2"):
+        monkeypatch.delenv("SCHW_FULL_RAYS", raising=False)
+        if mode:
+            monkeypatch.setenv("SCHW_FULL_RAYS", mode)
+        traj, rows = handle.integrate_batch_full(q0, p0, steps, sc.delta, 2.0 * sc.mass, sc.r_max, 1.0, want_rows=True)
+        outs[mode] = (traj, rows, handle.last_counters())
+    for mode in ("1", "2"):
+        assert np.array_equal(outs[mode][0], outs[""][0]) and np.array_equal(outs[mode][1], outs[""][1])
+    assert (outs[""][1] == steps).all()
+    # the default took the same kernel as the forced two-ray one, not the one-ray one (padding of the last CTA differs)
+    assert outs[""][2][1] == outs["2"][2][1] != outs["1"][2][1]
